@@ -1,0 +1,349 @@
+"""Tensor-level host wrappers over the C ABI (include/asr_b200.h).
+
+PyTorch is only the plumbing here: it owns device memory and the CUDA stream;
+every computation is one of the library's hand-written kernels.  All tensors must
+live on the current CUDA device; a CPU tensor raises (there is no fallback).
+"""
+import ctypes as C
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from ._lib import check, lib
+
+_i64 = C.c_int64
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _cuda(t, dtype, name):
+    if not isinstance(t, torch.Tensor):
+        raise ValueError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("asr_b200: %s is on %s — the hot path runs on CUDA only (no CPU fallback)" %
+                           (name, t.device))
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    t = t.detach().contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    return t
+
+
+def _opt(t, dtype, name):
+    if t is None or t.numel() == 0:
+        return None
+    return _cuda(t, dtype, name)
+
+
+# ------------------------------------------------------------------------------------ octree / grids
+
+GRID_FIELDS = ("voxel_keys", "voxel_centers", "voxel_sizes", "neighbors_index", "neighbors_kernel_index",
+               "neighbors_row_splits", "up_neighbors_index", "up_neighbors_kernel_index", "up_neighbors_row_splits")
+
+
+class Octree:
+    """Opaque octree handle (mirror of the python module's `Octree`, module.cpp:282),
+    built on the GPU by asr_octree_create (reference CreateOctreeFromPoints, octree.cpp:230)."""
+
+    def __init__(self, points, radii, bb_min, bb_max, radius_scale=1.0, grow_steps=0, max_depth=21):
+        points = _cuda(points, torch.float32, "points")
+        radii = _cuda(radii, torch.float32, "radii")
+        if points.ndim != 2 or points.shape[1] != 3:
+            raise ValueError("points must have shape [N,3]")
+        if radii.ndim != 1 or radii.shape[0] != points.shape[0]:
+            raise ValueError("radii must have shape [N]")
+        bb_min = np.ascontiguousarray(np.asarray(bb_min, dtype=np.float32).reshape(3))
+        bb_max = np.ascontiguousarray(np.asarray(bb_max, dtype=np.float32).reshape(3))
+        self.device = points.device
+        self._h = C.c_void_p(0)
+        check(lib().asr_octree_create(_ptr(points), _ptr(radii), points.shape[0], bb_min.ctypes.data,
+                                      bb_max.ctypes.data, float(radius_scale), int(grow_steps), int(max_depth),
+                                      _stream(), C.byref(self._h)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().asr_octree_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    @property
+    def num_leaves(self):
+        return int(lib().asr_octree_num_leaves(self._h))
+
+    @property
+    def num_nodes(self):
+        return int(lib().asr_octree_num_nodes(self._h))
+
+    @property
+    def balance_rounds(self):
+        return int(lib().asr_octree_balance_rounds(self._h))
+
+    def leaves(self):
+        out = torch.empty(self.num_leaves, dtype=torch.int64, device=self.device)
+        check(lib().asr_octree_get_leaves(self._h, _ptr(out), _stream()))
+        return out  # bit pattern of the uint64 location codes
+
+    def frame(self):
+        vs = np.empty(22, np.float32)
+        ivs = np.empty(22, np.float32)
+        off = np.empty(3, np.int32)
+        check(lib().asr_octree_get_frame(self._h, vs.ctypes.data, ivs.ctypes.data, off.ctypes.data))
+        return vs, ivs, off
+
+    def grids(self, num_levels, voxel_info_all_levels=False):
+        """asr_grids_* (reference CreateGridsFromOctree, grid.cpp:245).  Returns a
+        list (finest first) of dicts of CUDA tensors with the key set of
+        pyCreateGridsFromOctree (module.cpp:163-228); voxel_keys is int64 holding
+        the uint64 bit pattern."""
+        L = lib()
+        check(L.asr_grids_build(self._h, int(num_levels), int(bool(voxel_info_all_levels)), _stream()))
+        dev = self.device
+        res = []
+        for lev in range(num_levels):
+            V, E = _i64(0), _i64(0)
+            check(L.asr_grids_level_size(self._h, lev, C.byref(V), C.byref(E)))
+            V, E = V.value, E.value
+            info = lev == 0 or voxel_info_all_levels
+            up = lev < num_levels - 1
+            g = {}
+            if info:
+                g["voxel_keys"] = torch.empty(V, dtype=torch.int64, device=dev)
+                g["voxel_centers"] = torch.empty((V, 3), dtype=torch.float32, device=dev)
+                g["voxel_sizes"] = torch.empty(V, dtype=torch.float32, device=dev)
+            g["neighbors_index"] = torch.empty(E, dtype=torch.int32, device=dev)
+            g["neighbors_kernel_index"] = torch.empty(E, dtype=torch.uint8, device=dev)
+            g["neighbors_row_splits"] = torch.empty(V + 1, dtype=torch.int64, device=dev)
+            if up:
+                g["up_neighbors_index"] = torch.empty(V, dtype=torch.int32, device=dev)
+                g["up_neighbors_kernel_index"] = torch.empty(V, dtype=torch.uint8, device=dev)
+                g["up_neighbors_row_splits"] = torch.empty(V + 1, dtype=torch.int64, device=dev)
+            check(L.asr_grids_get(self._h, lev, *[_ptr(g.get(k)) for k in GRID_FIELDS], _stream()))
+            # the reference omits empty vectors from the dict (module.cpp:174-223)
+            res.append({k: v for k, v in g.items() if v.numel() > 0})
+        return res
+
+    def dual_vertex_indices(self):
+        """[num_duals, 8] int64 leaf indices (reference CreateDualVertexIndices, grid.cpp:450)."""
+        n = _i64(0)
+        check(lib().asr_duals_count(self._h, C.byref(n), _stream()))
+        out = torch.empty((n.value, 8), dtype=torch.int64, device=self.device)
+        check(lib().asr_duals_fill(self._h, _ptr(out), _stream()))
+        return out
+
+
+# ------------------------------------------------------------------------------------ aggregation search
+
+
+def multi_radius_search(points, queries, radii):
+    """(index int32[P], squared distance float32[P], row_splits int64[Q+1]);
+    d2 < r^2, ascending by d2 (reference nsearch.cpp:130-146)."""
+    points = _cuda(points, torch.float32, "points")
+    queries = _cuda(queries, torch.float32, "queries")
+    radii = _cuda(radii, torch.float32, "radii")
+    if points.ndim != 2 or points.shape[1] != 3 or queries.ndim != 2 or queries.shape[1] != 3:
+        raise ValueError("points and queries must have shape [N,3]")
+    if radii.shape != (queries.shape[0],):
+        raise ValueError("radii must have shape [num_queries]")
+    h, n = C.c_void_p(0), _i64(0)
+    L = lib()
+    check(L.asr_radius_search_create(_ptr(points), points.shape[0], _ptr(queries), _ptr(radii), queries.shape[0],
+                                     _stream(), C.byref(h), C.byref(n)))
+    try:
+        dev = points.device
+        idx = torch.empty(n.value, dtype=torch.int32, device=dev)
+        dist = torch.empty(n.value, dtype=torch.float32, device=dev)
+        rs = torch.empty(queries.shape[0] + 1, dtype=torch.int64, device=dev)
+        check(L.asr_radius_search_fill(h, _ptr(idx), _ptr(dist), _ptr(rs), _stream()))
+    finally:
+        L.asr_radius_search_destroy(h)
+    return idx, dist, rs
+
+
+def scale_compatibility(voxel_sizes, point_radii, neighbors_index, neighbors_row_splits):
+    voxel_sizes = _cuda(voxel_sizes, torch.float32, "voxel_sizes")
+    point_radii = _cuda(point_radii, torch.float32, "point_radii")
+    idx = _cuda(neighbors_index, torch.int32, "neighbors_index")
+    rs = _cuda(neighbors_row_splits, torch.int64, "neighbors_row_splits")
+    out = torch.empty(idx.shape[0], dtype=torch.float32, device=idx.device)
+    check(lib().asr_scale_compatibility(_ptr(voxel_sizes), _ptr(point_radii), _ptr(idx), _ptr(rs),
+                                        voxel_sizes.shape[0], _ptr(out), _stream()))
+    return out
+
+
+def aggregation_importance(scale_compat, dist):
+    scale_compat = _cuda(scale_compat, torch.float32, "scale_compat")
+    dist = _cuda(dist, torch.float32, "dist")
+    out = torch.empty_like(dist)
+    check(lib().asr_aggregation_importance(_ptr(scale_compat), _ptr(dist), dist.shape[0], _ptr(out), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------ convolutions
+
+
+def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_features, inp_importance,
+                    neighbors_index, neighbors_importance, neighbors_row_splits, normalize=True, bias=None,
+                    relu=False):
+    filters = _cuda(filters, torch.float32, "filters")
+    if filters.ndim != 5 or not (filters.shape[0] == filters.shape[1] == filters.shape[2]):
+        raise ValueError("filters must have shape [S,S,S,Cin,Cout]")
+    S, _, _, Cin, Cout = filters.shape
+    out_positions = _cuda(out_positions, torch.float32, "out_positions")
+    extents = _cuda(extents, torch.float32, "extents").reshape(-1)
+    V = out_positions.shape[0]
+    if extents.numel() not in (1, V):
+        raise ValueError("extents must have 1 or num_out elements")
+    inp_positions = _cuda(inp_positions, torch.float32, "inp_positions")
+    inp_features = _cuda(inp_features, torch.float32, "inp_features")
+    if inp_features.shape[1] != Cin:
+        raise ValueError("inp_features channel count does not match the filter")
+    idx = _cuda(neighbors_index, torch.int32, "neighbors_index")
+    rs = _cuda(neighbors_row_splits, torch.int64, "neighbors_row_splits")
+    if rs.shape[0] != V + 1:
+        raise ValueError("neighbors_row_splits must have num_out+1 elements")
+    out = torch.empty((V, Cout), dtype=torch.float32, device=filters.device)
+    check(lib().asr_continuous_conv(
+        _ptr(filters), _ptr(out_positions), _ptr(extents), 1 if extents.numel() == V and V != 1 else 0,
+        _ptr(_opt(offset, torch.float32, "offset")), _ptr(inp_positions), _ptr(inp_features),
+        _ptr(_opt(inp_importance, torch.float32, "inp_importance")), _ptr(idx),
+        _ptr(_opt(neighbors_importance, torch.float32, "neighbors_importance")), _ptr(rs), V, S, Cin, Cout,
+        int(bool(normalize)), _ptr(_opt(bias, torch.float32, "bias")), int(bool(relu)), _ptr(out), _stream()))
+    return out
+
+
+class ConvPlan:
+    """Slot-sorted form of one neighbour table; build once, reuse for every conv on it."""
+
+    def __init__(self, neighbors_index, neighbors_kernel_index, neighbors_row_splits, kernel_size):
+        self.idx = _cuda(neighbors_index, torch.int32, "neighbors_index")
+        self.slot = _cuda(neighbors_kernel_index, torch.uint8, "neighbors_kernel_index")
+        self.row_splits = _cuda(neighbors_row_splits, torch.int64, "neighbors_row_splits")
+        if self.idx.shape != self.slot.shape:
+            raise ValueError("neighbors_index and neighbors_kernel_index must have the same length")
+        self.num_out = self.row_splits.shape[0] - 1
+        self.kernel_size = int(kernel_size)
+        self._h = C.c_void_p(0)
+        check(lib().asr_conv_plan_create(_ptr(self.idx), _ptr(self.slot), _ptr(self.row_splits), self.num_out,
+                                         self.idx.shape[0], self.kernel_size, _stream(), C.byref(self._h)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().asr_conv_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+
+def sparse_conv(plan, filters, inp_features, inp_importance=None, neighbors_importance=None, importance_col=0,
+                normalize=False, normalize_col=0, normalizer=None, bias=None, relu=False):
+    """out[o] = sum_n imp_n * x[idx_n] @ filters[slot_n] (+ normalise, bias, ReLU)."""
+    filters = _cuda(filters, torch.float32, "filters")
+    x = _cuda(inp_features, torch.float32, "inp_features")
+    K, Cin, Cout = filters.shape
+    if K != plan.kernel_size:
+        raise ValueError("filters.shape[0] does not match the plan's kernel size")
+    if x.shape[1] != Cin:
+        raise ValueError("inp_features channel count does not match the filter")
+    out = torch.empty((plan.num_out, Cout), dtype=torch.float32, device=x.device)
+    check(lib().asr_sparse_conv(plan._h, _ptr(filters), _ptr(x), Cin, Cout,
+                                _ptr(_opt(inp_importance, torch.float32, "inp_importance")),
+                                _ptr(_opt(neighbors_importance, torch.float32, "neighbors_importance")),
+                                int(importance_col), int(bool(normalize)), int(normalize_col),
+                                _ptr(_opt(normalizer, torch.float32, "normalizer")), _ptr(plan.row_splits),
+                                _ptr(_opt(bias, torch.float32, "bias")), int(bool(relu)), _ptr(out), _stream()))
+    return out
+
+
+def reduce_subarrays_sum(values, row_splits, index=None):
+    values = _cuda(values, torch.float32, "values")
+    rs = _cuda(row_splits, torch.int64, "row_splits")
+    idx = _opt(index, torch.int32, "index")
+    out = torch.empty(rs.shape[0] - 1, dtype=torch.float32, device=values.device)
+    check(lib().asr_reduce_subarrays_sum(_ptr(values), _ptr(idx), _ptr(rs), rs.shape[0] - 1, _ptr(out), _stream()))
+    return out
+
+
+InvertNeighborsListResult = namedtuple("InvertNeighborsListResult",
+                                       ["neighbors_index", "neighbors_row_splits", "neighbors_attributes"])
+
+
+def invert_neighbors_list(num_points, inp_neighbors_index, inp_neighbors_row_splits, inp_neighbors_attributes):
+    idx = _cuda(inp_neighbors_index, torch.int32, "inp_neighbors_index")
+    rs = _cuda(inp_neighbors_row_splits, torch.int64, "inp_neighbors_row_splits")
+    attrs = inp_neighbors_attributes
+    has_attr = attrs is not None and attrs.numel() > 0
+    if has_attr:
+        attrs = _cuda(attrs, attrs.dtype, "inp_neighbors_attributes")
+        if attrs.shape[0] != idx.shape[0]:
+            raise ValueError("attributes must have one entry per neighbour")
+    dev = idx.device
+    out_idx = torch.empty_like(idx)
+    out_rs = torch.empty(num_points + 1, dtype=torch.int64, device=dev)
+    out_attr = torch.empty_like(attrs) if has_attr else torch.empty(0, dtype=torch.float32, device=dev)
+    abytes = attrs.element_size() * int(np.prod(attrs.shape[1:])) if has_attr else 0
+    check(lib().asr_invert_neighbors_list(int(num_points), _ptr(idx), _ptr(rs), rs.shape[0] - 1, idx.shape[0],
+                                          _ptr(attrs if has_attr else None), abytes, _ptr(out_idx), _ptr(out_rs),
+                                          _ptr(out_attr if has_attr else None), _stream()))
+    return InvertNeighborsListResult(out_idx, out_rs, out_attr)
+
+
+# ------------------------------------------------------------------------------------ decode / contouring
+
+
+def decode(shifts, code, w1, b1, w2, b2, w3, signed_scale=None, with_gradient=False):
+    code = _cuda(code, torch.float32, "code")
+    if code.ndim != 2 or code.shape[1] != 32:
+        raise ValueError("code must have shape [V,32]")
+    V = code.shape[0]
+    shifts = _opt(shifts, torch.float32, "shifts")
+    if shifts is not None and shifts.shape != (V, 3):
+        raise ValueError("shifts must have shape [V,3]")
+    ws = [_cuda(w, torch.float32, "decoder weight") for w in (w1, b1, w2, b2, w3)]
+    if ws[0].shape != (32, 35) or ws[2].shape != (32, 32) or ws[4].shape != (2, 32):
+        raise ValueError("decoder weights must have shapes [32,35], [32,32], [2,32]")
+    values = torch.empty((V, 2), dtype=torch.float32, device=code.device)
+    grad = torch.empty((V, 3), dtype=torch.float32, device=code.device) if with_gradient else None
+    check(lib().asr_decode(_ptr(shifts), _ptr(code), V, *[_ptr(w) for w in ws],
+                           _ptr(_opt(signed_scale, torch.float32, "signed_scale")), _ptr(values), _ptr(grad),
+                           _stream()))
+    return (values, grad) if with_gradient else values
+
+
+def contour_vertices(values, dual_indices, node_positions, unsigned_threshold=1.0):
+    """Vertex part of CreateTriangleMesh (contouring.cpp:66-199).  Returns
+    (vertices f32[M,3], dual index of each vertex i64[M])."""
+    values = _cuda(values, torch.float32, "values")
+    duals = _cuda(dual_indices, torch.int64, "dual_indices")
+    pos = _cuda(node_positions, torch.float32, "node_positions")
+    if values.ndim != 2 or values.shape[1] != 2:
+        raise RuntimeError("values vector size is not a multiple of 2.")
+    if duals.ndim != 2 or duals.shape[1] != 8:
+        raise RuntimeError("dual_indices vector size is not a multiple of 8.")
+    if pos.ndim != 2 or pos.shape[1] != 3:
+        raise RuntimeError("node_positions vector size is not a multiple of 3.")
+    D = duals.shape[0]
+    dev = values.device
+    flag = torch.empty(D, dtype=torch.uint8, device=dev)
+    offset = torch.empty(D + 1, dtype=torch.int64, device=dev)
+    n = _i64(0)
+    L = lib()
+    check(L.asr_contour_count(_ptr(values), _ptr(duals), D, float(unsigned_threshold), _ptr(flag), _ptr(offset),
+                              C.byref(n), _stream()))
+    verts = torch.empty((n.value, 3), dtype=torch.float32, device=dev)
+    vdual = torch.empty(n.value, dtype=torch.int64, device=dev)
+    check(L.asr_contour_fill(_ptr(values), _ptr(duals), D, float(unsigned_threshold), _ptr(pos), _ptr(flag),
+                             _ptr(offset), _ptr(verts), _ptr(vdual), _stream()))
+    return verts, vdual

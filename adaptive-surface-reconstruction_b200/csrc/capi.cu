@@ -1,0 +1,263 @@
+// extern "C" surface of libasr_b200.so — see include/asr_b200.h for the contract
+// and the reference interfaces each entry point replaces.
+#include "../../include/asr_b200.h"
+
+#include "internal.h"
+#include "search.h"
+#include "sparse_conv.h"
+
+namespace asrb {
+std::atomic<long long> g_kernel_launches{0};
+
+void continuous_conv(const float* filters, const float* out_pos, const float* extents, int extents_stride,
+                     const float* offset, const float* inp_pos, const float* inp_feat, const float* inp_importance,
+                     const int32_t* nidx, const float* nimp, const int64_t* splits, int64_t V, int S, int Cin, int Cout,
+                     int normalize, const float* bias, int relu, float* out, cudaStream_t s);
+void aggregation_importance(const float* compat, const float* d2, int64_t n, float* out, cudaStream_t s);
+void decode_mlp(const float* shifts, const float* code, int64_t V, const float* w1, const float* b1, const float* w2,
+                const float* b2, const float* w3, const float* signed_scale, float* values, float* grad,
+                cudaStream_t s);
+void contour_count(const float* values, const int64_t* duals, int64_t D, float thr, uint8_t* flag, int64_t* offset,
+                   int64_t* num_vertices, cudaStream_t s);
+void contour_fill(const float* values, const int64_t* duals, int64_t D, float thr, const float* pos,
+                  const uint8_t* flag, const int64_t* offset, float* vertices, int64_t* vertex_dual, cudaStream_t s);
+void invert_neighbors_list(int64_t num_points, const int32_t* idx, const int64_t* splits, int64_t Q, int64_t E,
+                           const void* attrs, int attr_bytes, int32_t* out_idx, int64_t* out_splits, void* out_attrs,
+                           cudaStream_t s);
+}  // namespace asrb
+
+using namespace asrb;
+
+struct asr_octree {
+    Octree t;
+};
+struct asr_search {
+    Search s;
+};
+struct asr_conv_plan {
+    ConvPlan p;
+};
+
+namespace {
+thread_local std::string g_error;
+
+template <class F>
+int guarded(F&& f) {
+    try {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+            throw Error(kCudaError, "asr_b200: no CUDA device available (there is no CPU fallback)");
+        f();
+        return kOk;
+    } catch (const Error& e) {
+        g_error = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return kRuntimeError;
+    }
+}
+inline cudaStream_t S(void* stream) { return (cudaStream_t)stream; }
+
+template <class T>
+void copy_out(T* dst, const DevBuf<T>& src, size_t n, cudaStream_t s) {
+    if (dst && n) ASRB_CUDA(cudaMemcpyAsync(dst, src.get(), n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+}
+
+__global__ void iota_i64_kernel(int64_t* out, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
+}
+}  // namespace
+
+extern "C" {
+
+int asr_version(void) { return ASR_B200_VERSION; }
+const char* asr_last_error(void) { return g_error.c_str(); }
+int64_t asr_kernel_launches(void) { return (int64_t)g_kernel_launches.load(); }
+
+int asr_octree_create(const float* d_points, const float* d_radii, int64_t num_points, const float h_bb_min[3],
+                      const float h_bb_max[3], float radius_scale, int grow_steps, int max_depth, void* stream,
+                      asr_octree** out) {
+    return guarded([&] {
+        ASRB_REQUIRE(out != nullptr, "out must not be null");
+        ASRB_REQUIRE(num_points >= 0, "num_points must be >= 0");
+        ASRB_REQUIRE(grow_steps == 0, "grow_steps must be 0 (the only value the reference pipeline uses)");
+        ASRB_REQUIRE(num_points == 0 || (d_points && d_radii), "points/radii must not be null");
+        auto h = std::make_unique<asr_octree>();
+        h->t.frame = make_frame(h_bb_min, h_bb_max);
+        cudaGetDevice(&h->t.device);
+        octree_build(h->t, d_points, d_radii, num_points, radius_scale, max_depth, S(stream));
+        *out = h.release();
+    });
+}
+void asr_octree_destroy(asr_octree* tree) { delete tree; }
+int64_t asr_octree_num_leaves(const asr_octree* tree) { return tree ? tree->t.num_leaves : 0; }
+int64_t asr_octree_num_nodes(const asr_octree* tree) { return tree ? tree->t.num_nodes : 0; }
+int asr_octree_balance_rounds(const asr_octree* tree) { return tree ? tree->t.balance_rounds : 0; }
+int asr_octree_get_leaves(const asr_octree* tree, uint64_t* d_out, void* stream) {
+    return guarded([&] {
+        ASRB_REQUIRE(tree, "tree is null");
+        copy_out((Key*)d_out, tree->t.leaves, (size_t)tree->t.num_leaves, S(stream));
+    });
+}
+int asr_octree_get_frame(const asr_octree* tree, float* vs, float* ivs, int32_t* off) {
+    return guarded([&] {
+        ASRB_REQUIRE(tree, "tree is null");
+        for (int l = 0; l <= kMaxLevel; ++l) {
+            if (vs) vs[l] = tree->t.frame.vs[l];
+            if (ivs) ivs[l] = tree->t.frame.ivs[l];
+        }
+        if (off)
+            for (int a = 0; a < 3; ++a) off[a] = tree->t.frame.off[a];
+    });
+}
+
+int asr_grids_build(asr_octree* tree, int num_levels, int voxel_info_all_levels, void* stream) {
+    return guarded([&] {
+        ASRB_REQUIRE(tree, "tree is null");
+        grids_build(tree->t, num_levels, voxel_info_all_levels != 0, S(stream));
+    });
+}
+int asr_grids_level_size(const asr_octree* tree, int level, int64_t* num_voxels, int64_t* num_neighbors) {
+    return guarded([&] {
+        ASRB_REQUIRE(tree, "tree is null");
+        ASRB_REQUIRE(level >= 0 && level < (int)tree->t.grids.size(), "level out of range (call asr_grids_build first)");
+        if (num_voxels) *num_voxels = tree->t.grids[level]->V;
+        if (num_neighbors) *num_neighbors = tree->t.grids[level]->E;
+    });
+}
+int asr_grids_get(const asr_octree* tree, int level, uint64_t* keys, float* centers, float* sizes, int32_t* nidx,
+                  uint8_t* nslot, int64_t* nsplits, int32_t* uidx, uint8_t* uslot, int64_t* usplits, void* stream) {
+    return guarded([&] {
+        ASRB_REQUIRE(tree, "tree is null");
+        ASRB_REQUIRE(level >= 0 && level < (int)tree->t.grids.size(), "level out of range (call asr_grids_build first)");
+        const GridLevel& g = *tree->t.grids[level];
+        cudaStream_t s = S(stream);
+        const size_t V = (size_t)g.V, E = (size_t)g.E;
+        copy_out((Key*)keys, g.keys, V, s);
+        if (centers || sizes) ASRB_REQUIRE(g.centers.size() == 3 * V, "voxel info was not built for this level");
+        copy_out(centers, g.centers, 3 * V, s);
+        copy_out(sizes, g.sizes, V, s);
+        copy_out(nidx, g.nidx, E, s);
+        copy_out(nslot, g.nslot, E, s);
+        copy_out(nsplits, g.nsplits, V + 1, s);
+        if (uidx || uslot || usplits) ASRB_REQUIRE(g.has_up, "the last level has no up table");
+        copy_out(uidx, g.uidx, V, s);
+        copy_out(uslot, g.uslot, V, s);
+        if (usplits) {
+            iota_i64_kernel<<<grid_for(V + 1, 256), 256, 0, s>>>(usplits, (long long)V + 1);
+            ASRB_CHECK_LAUNCH();
+        }
+    });
+}
+
+int asr_duals_count(asr_octree* tree, int64_t* num_duals, void* stream) {
+    return guarded([&] {
+        ASRB_REQUIRE(tree && num_duals, "null argument");
+        duals_count(tree->t, S(stream));
+        *num_duals = tree->t.num_duals;
+    });
+}
+int asr_duals_fill(asr_octree* tree, int64_t* d_out, void* stream) {
+    return guarded([&] {
+        ASRB_REQUIRE(tree, "tree is null");
+        duals_fill(tree->t, d_out, S(stream));
+    });
+}
+
+int asr_radius_search_create(const float* d_points, int64_t num_points, const float* d_queries, const float* d_radii,
+                             int64_t num_queries, void* stream, asr_search** out, int64_t* num_pairs) {
+    return guarded([&] {
+        ASRB_REQUIRE(out && num_pairs, "null argument");
+        ASRB_REQUIRE(num_points >= 0 && num_queries >= 0, "negative size");
+        ASRB_REQUIRE(num_points < (int64_t(1) << 31), "too many points");
+        auto h = std::make_unique<asr_search>();
+        search_prepare(h->s, d_points, num_points, d_queries, d_radii, num_queries, S(stream));
+        *num_pairs = h->s.num_pairs;
+        *out = h.release();
+    });
+}
+int asr_radius_search_fill(asr_search* search, int32_t* idx, float* dist, int64_t* splits, void* stream) {
+    return guarded([&] {
+        ASRB_REQUIRE(search && splits, "null argument");
+        search_fill(search->s, idx, dist, splits, S(stream));
+    });
+}
+void asr_radius_search_destroy(asr_search* search) { delete search; }
+
+int asr_scale_compatibility(const float* sizes, const float* radii, const int32_t* idx, const int64_t* splits,
+                            int64_t num_queries, float* out, void* stream) {
+    return guarded([&] { scale_compat(sizes, radii, idx, splits, num_queries, out, S(stream)); });
+}
+int asr_aggregation_importance(const float* compat, const float* dist, int64_t n, float* out, void* stream) {
+    return guarded([&] { aggregation_importance(compat, dist, n, out, S(stream)); });
+}
+
+int asr_continuous_conv(const float* filters, const float* out_pos, const float* extents, int extents_stride,
+                        const float* offset, const float* inp_pos, const float* inp_feat, const float* inp_importance,
+                        const int32_t* nidx, const float* nimp, const int64_t* splits, int64_t num_out, int kernel_size,
+                        int in_channels, int out_channels, int normalize, const float* bias, int relu, float* out,
+                        void* stream) {
+    return guarded([&] {
+        ASRB_REQUIRE(kernel_size >= 1 && in_channels >= 1 && out_channels >= 1, "bad filter shape");
+        ASRB_REQUIRE(extents_stride == 0 || extents_stride == 1, "extents_stride must be 0 or 1");
+        continuous_conv(filters, out_pos, extents, extents_stride, offset, inp_pos, inp_feat, inp_importance, nidx, nimp,
+                        splits, num_out, kernel_size, in_channels, out_channels, normalize, bias, relu, out, S(stream));
+    });
+}
+
+int asr_conv_plan_create(const int32_t* idx, const uint8_t* slot, const int64_t* splits, int64_t num_out,
+                         int64_t num_entries, int kernel_size, void* stream, asr_conv_plan** out) {
+    return guarded([&] {
+        ASRB_REQUIRE(out, "null argument");
+        auto h = std::make_unique<asr_conv_plan>();
+        conv_plan_build(h->p, idx, slot, splits, num_out, num_entries, kernel_size, S(stream));
+        *out = h.release();
+    });
+}
+void asr_conv_plan_destroy(asr_conv_plan* plan) { delete plan; }
+
+int asr_sparse_conv(const asr_conv_plan* plan, const float* filters, const float* x, int in_channels, int out_channels,
+                    const float* inp_importance, const float* neighbors_importance, int importance_col, int normalize,
+                    int normalize_col, const float* normalizer, const int64_t* splits, const float* bias, int relu,
+                    float* out, void* stream) {
+    return guarded([&] {
+        ASRB_REQUIRE(plan, "plan is null");
+        ASRB_REQUIRE(!normalize || normalizer || splits, "normalize needs a normalizer or the row splits");
+        sparse_conv_forward(plan->p, x, filters, in_channels, out_channels, inp_importance, neighbors_importance,
+                            importance_col, normalize, normalize_col, normalizer, splits, bias, relu, out, S(stream));
+    });
+}
+int asr_reduce_subarrays_sum(const float* values, const int32_t* index, const int64_t* splits, int64_t num_rows,
+                             float* out, void* stream) {
+    return guarded([&] { row_importance(values, index, splits, num_rows, out, S(stream)); });
+}
+int asr_invert_neighbors_list(int64_t num_points, const int32_t* idx, const int64_t* splits, int64_t num_queries,
+                              int64_t num_entries, const void* attrs, int attr_bytes, int32_t* out_idx,
+                              int64_t* out_splits, void* out_attrs, void* stream) {
+    return guarded([&] {
+        ASRB_REQUIRE(num_points >= 0 && num_entries >= 0, "negative size");
+        invert_neighbors_list(num_points, idx, splits, num_queries, num_entries, attrs, attr_bytes, out_idx, out_splits,
+                              out_attrs, S(stream));
+    });
+}
+
+int asr_decode(const float* shifts, const float* code, int64_t V, const float* w1, const float* b1, const float* w2,
+               const float* b2, const float* w3, const float* signed_scale, float* values, float* grad, void* stream) {
+    return guarded([&] { decode_mlp(shifts, code, V, w1, b1, w2, b2, w3, signed_scale, values, grad, S(stream)); });
+}
+
+int asr_contour_count(const float* values, const int64_t* duals, int64_t D, float thr, uint8_t* flag, int64_t* offset,
+                      int64_t* num_vertices, void* stream) {
+    return guarded([&] {
+        ASRB_REQUIRE(num_vertices, "null argument");
+        contour_count(values, duals, D, thr, flag, offset, num_vertices, S(stream));
+    });
+}
+int asr_contour_fill(const float* values, const int64_t* duals, int64_t D, float thr, const float* pos,
+                     const uint8_t* flag, const int64_t* offset, float* vertices, int64_t* vertex_dual, void* stream) {
+    return guarded([&] { contour_fill(values, duals, D, thr, pos, flag, offset, vertices, vertex_dual, S(stream)); });
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// Continuous convolution (points -> voxel features), the aggregation step.
+//
+// Replaces Open3D-ML's `continuous_conv` op as the reference uses it through
+// ml3d.layers.ContinuousConv (models/v0/net_definitions_torch.py:53-70,108-116):
+// coordinate_mapping='ball_to_cube_radial', align_corners=True,
+// interpolation='linear', normalize=True, user-supplied neighbour lists with a
+// per-pair importance.  Open3D builds a dense [S^3*Cin x 32-voxel] matrix per
+// block and calls an Eigen GEMM; here one warp owns one output voxel, keeps the
+// S^3 x Cin cell tensor in shared memory, splats each neighbour with its 8
+// trilinear taps (lane = tap x channel, so a pair is one conflict-free
+// shared-memory update), and contracts with the filter in registers
+// (lane = output channel).  Bias and ReLU of the layer are fused.
+#include "internal.h"
+
+namespace asrb {
+
+constexpr int kCcWarps = 8;
+
+__global__ void __launch_bounds__(kCcWarps * 32)
+cconv_kernel(const float* __restrict__ filters,  // [S,S,S,Cin,Cout]  (z,y,x order)
+             const float* __restrict__ out_pos, const float* __restrict__ extents, int extents_stride,
+             const float* __restrict__ offset, const float* __restrict__ inp_pos,
+             const float* __restrict__ inp_feat, const float* __restrict__ inp_importance,
+             const int32_t* __restrict__ nidx, const float* __restrict__ nimp,
+             const int64_t* __restrict__ splits, long long V, int S, int Cin, int Cout, int normalize,
+             const float* __restrict__ bias, int relu, float* __restrict__ out) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cells = S * S * S;
+    float* B = smem + (size_t)warp * cells * Cin;
+    const long long v = blockIdx.x * (long long)kCcWarps + warp;
+    if (v >= V) return;
+    for (int j = lane; j < cells * Cin; j += 32) B[j] = 0.f;
+    __syncwarp();
+    const float cx = out_pos[3 * v], cy = out_pos[3 * v + 1], cz = out_pos[3 * v + 2];
+    const float scale = 2.0f / extents[v * extents_stride];
+    const float ox = offset ? offset[0] : 0.f, oy = offset ? offset[1] : 0.f, oz = offset ? offset[2] : 0.f;
+    const float sm1 = (float)(S - 1);
+    float norm = 0.f;
+    const int64_t e = splits[v + 1];
+    for (int64_t n = splits[v]; n < e; ++n) {
+        const int p = nidx[n];
+        float imp = nimp ? nimp[n] : 1.0f;
+        norm += imp;
+        if (inp_importance) imp *= inp_importance[p];
+        // relative position -> unit ball -> cube [-0.5, 0.5]^3 -> kernel coordinates
+        float x = (inp_pos[3 * (size_t)p] - cx) * scale;
+        float y = (inp_pos[3 * (size_t)p + 1] - cy) * scale;
+        float z = (inp_pos[3 * (size_t)p + 2] - cz) * scale;
+        const float nrm = sqrtf(x * x + y * y + z * z);
+        const float amax = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+        const float stretch = amax < 1e-8f ? 0.f : 0.5f * nrm / amax;
+        x = fminf(fmaxf((x * stretch + ox + 0.5f) * sm1, 0.f), sm1);
+        y = fminf(fmaxf((y * stretch + oy + 0.5f) * sm1, 0.f), sm1);
+        z = fminf(fmaxf((z * stretch + oz + 0.5f) * sm1, 0.f), sm1);
+        const int x0 = min((int)x, S - 1), y0 = min((int)y, S - 1), z0 = min((int)z, S - 1);
+        const float ax = x - (float)x0, ay = y - (float)y0, az = z - (float)z0;
+        for (int it = lane; it < 8 * Cin; it += 32) {
+            const int tap = it / Cin, ch = it - tap * Cin;
+            const int tx = tap & 1, ty = (tap >> 1) & 1, tz = tap >> 2;
+            // a "+1" tap that is clamped onto its "+0" twin carries weight 0: skip
+            if ((tx && x0 == S - 1) || (ty && y0 == S - 1) || (tz && z0 == S - 1)) continue;
+            const float w = (tx ? ax : 1.f - ax) * (ty ? ay : 1.f - ay) * (tz ? az : 1.f - az);
+            const int cell = ((z0 + tz) * S + (y0 + ty)) * S + (x0 + tx);
+            B[cell * Cin + ch] += w * (inp_feat[(size_t)p * Cin + ch] * imp);
+        }
+        __syncwarp();
+    }
+    const int K = cells * Cin;
+    for (int oc = lane; oc < Cout; oc += 32) {
+        float acc = 0.f;
+        for (int j = 0; j < K; ++j) acc = fmaf(B[j], __ldg(filters + (size_t)j * Cout + oc), acc);
+        if (normalize && norm != 0.f) acc /= norm;
+        if (bias) acc += bias[oc];
+        if (relu) acc = fmaxf(acc, 0.f);
+        out[(size_t)v * Cout + oc] = acc;
+    }
+}
+
+// importance = scale_compat * clamp((1 - d2)^3, 0, 1)
+// (CConvAggregationBlock.forward, net_definitions_torch.py:107; window_poly6 common_torch.py:21)
+__global__ void __launch_bounds__(256)
+importance_kernel(const float* __restrict__ compat, const float* __restrict__ d2, long long n, float* __restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float t = 1.0f - d2[i];
+    out[i] = compat[i] * fminf(fmaxf(t * t * t, 0.f), 1.f);
+}
+
+void continuous_conv(const float* filters, const float* out_pos, const float* extents, int extents_stride,
+                     const float* offset, const float* inp_pos, const float* inp_feat, const float* inp_importance,
+                     const int32_t* nidx, const float* nimp, const int64_t* splits, int64_t V, int S, int Cin, int Cout,
+                     int normalize, const float* bias, int relu, float* out, cudaStream_t s) {
+    if (V == 0) return;
+    const size_t smem = (size_t)kCcWarps * S * S * S * Cin * sizeof(float);
+    ASRB_REQUIRE(smem <= 200 * 1024, "continuous_conv: kernel_size^3 * in_channels too large for shared memory");
+    if (smem > 48 * 1024)
+        ASRB_CUDA(cudaFuncSetAttribute(cconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cconv_kernel<<<grid_for(V, kCcWarps), kCcWarps * 32, smem, s>>>(filters, out_pos, extents, extents_stride, offset,
+                                                                   inp_pos, inp_feat, inp_importance, nidx, nimp,
+                                                                   splits, V, S, Cin, Cout, normalize, bias, relu, out);
+    ASRB_CHECK_LAUNCH();
+}
+
+void aggregation_importance(const float* compat, const float* d2, int64_t n, float* out, cudaStream_t s) {
+    if (n == 0) return;
+    importance_kernel<<<grid_for(n, 256), 256, 0, s>>>(compat, d2, n, out);
+    ASRB_CHECK_LAUNCH();
+}
+
+}  // namespace asrb

@@ -1,0 +1,305 @@
+// Multi-radius neighbour search: for every query q_i, all points p with
+// |p - q_i|^2 < r_i^2, ascending by squared distance.
+//
+// Replaces the Open3D NearestNeighborSearch::MultiRadiusIndex/MultiRadiusSearch
+// calls (nanoflann KD-tree + TBB) made by
+// ComputeAggregationNeighborsAndScaleCompatibility (reference
+// cpp/lib/nsearch.cpp:107-162; Python twin models/v0/datareader.py:776-795).
+//
+// GPU design: points are binned on a 2^21-per-axis grid over their bounding cube
+// and sorted by Morton code once (radix sort), so every cubic cell of any
+// power-of-two size is one contiguous window of the sorted array.  One warp owns
+// a query: 16 lanes binary-search the window bounds of the <= 2x2x2 cells (edge
+// >= 2r) that cover the query ball, then all 32 lanes stream the concatenated
+// windows with coalesced 16-byte loads, test the strict squared distance and
+// compact hits with ballot/popc.  count -> scan -> fill -> per-row rank sort.
+//
+// Squared distances are evaluated as ((dx*dx) + dy*dy) + dz*dz in fp32 without
+// FMA contraction, the order nanoflann's L2 adaptor uses for dim 3, so that the
+// strict `<` test resolves boundary points identically.
+#include "internal.h"
+#include "prims.cuh"
+#include "search.h"
+
+namespace asrb {
+
+constexpr int kGridBits = 21;
+constexpr float kGridMax = 2097151.0f;  // 2^21 - 1
+
+struct BinFrame {
+    float origin[3];
+    float inv_h;
+};
+
+__device__ __forceinline__ int bin_coord(float x, float origin, float inv_h) {
+    float v = floorf(__fmul_rn(__fsub_rn(x, origin), inv_h));
+    v = fminf(fmaxf(v, 0.0f), kGridMax);  // monotone in x; NaN -> 0
+    return (int)v;
+}
+
+__device__ __forceinline__ unsigned ordered_bits(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float from_ordered_bits(unsigned u) {
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+
+// bounding box of the points: block reduction + 6 atomics per block
+__global__ void __launch_bounds__(256)
+bbox_kernel(const float* __restrict__ pts, long long n, unsigned* __restrict__ mn, unsigned* __restrict__ mx) {
+    unsigned lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0, 0, 0};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        for (int a = 0; a < 3; ++a) {
+            const float v = pts[3 * i + a];
+            if (v == v) {  // ignore NaN
+                const unsigned b = ordered_bits(v);
+                lo[a] = min(lo[a], b);
+                hi[a] = max(hi[a], b);
+            }
+        }
+    }
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = __reduce_min_sync(0xffffffffu, lo[a]);
+        hi[a] = __reduce_max_sync(0xffffffffu, hi[a]);
+    }
+    if ((threadIdx.x & 31) == 0)
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(mn + a, lo[a]);
+            atomicMax(mx + a, hi[a]);
+        }
+}
+
+__global__ void __launch_bounds__(256)
+point_code_kernel(const float* __restrict__ pts, long long n, BinFrame f, Key* __restrict__ codes,
+                  uint32_t* __restrict__ order) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = bin_coord(pts[3 * i], f.origin[0], f.inv_h);
+    const int y = bin_coord(pts[3 * i + 1], f.origin[1], f.inv_h);
+    const int z = bin_coord(pts[3 * i + 2], f.origin[2], f.inv_h);
+    codes[i] = morton3(x, y, z);
+    order[i] = (uint32_t)i;
+}
+
+// sorted position -> (x, y, z, original index) in one 16-byte record
+__global__ void __launch_bounds__(256)
+gather_points_kernel(const float* __restrict__ pts, const uint32_t* __restrict__ order, long long n,
+                     float4* __restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t j = order[i];
+    out[i] = make_float4(pts[3 * (size_t)j], pts[3 * (size_t)j + 1], pts[3 * (size_t)j + 2], __uint_as_float(j));
+}
+
+constexpr int kWarpsPerBlock = 8;
+
+template <bool FILL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+ball_query_kernel(const Key* __restrict__ codes, const float4* __restrict__ spts, long long n, BinFrame f,
+                  const float* __restrict__ queries, const float* __restrict__ radii, long long nq,
+                  int32_t* __restrict__ counts, const int64_t* __restrict__ splits,
+                  unsigned long long* __restrict__ out_keys) {
+    __shared__ long long s_begin[kWarpsPerBlock][8];
+    __shared__ int s_pre[kWarpsPerBlock][9];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long q = blockIdx.x * (long long)kWarpsPerBlock + warp;
+    if (q >= nq) return;
+    const float qx = queries[3 * q], qy = queries[3 * q + 1], qz = queries[3 * q + 2];
+    const float r = radii[q];
+    const float r2 = __fmul_rn(r, r);
+    // conservative integer box of the ball: pad by a few ulps of the coordinates
+    int lo[3], hi[3];
+    {
+        const float c[3] = {qx, qy, qz};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float pad = __fmaf_rn(r, 1.00001f, fabsf(c[a]) * 4e-7f);
+            lo[a] = bin_coord(c[a] - pad, f.origin[a], f.inv_h);
+            hi[a] = bin_coord(c[a] + pad, f.origin[a], f.inv_h);
+        }
+    }
+    // smallest power-of-two cell size that covers the box with <= 2 cells per axis
+    const int span = max(max(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]) + 1;
+    const int sh = span <= 1 ? 0 : 32 - __clz(span - 1);  // 2^sh >= span
+    long long pos = 0;
+    if (lane < 16) {
+        const int cell = lane >> 1;
+        const int cx = (lo[0] >> sh) + (cell & 1), cy = (lo[1] >> sh) + ((cell >> 1) & 1),
+                  cz = (lo[2] >> sh) + ((cell >> 2) & 1);
+        const bool valid = r >= 0.0f && cx <= (hi[0] >> sh) && cy <= (hi[1] >> sh) && cz <= (hi[2] >> sh);
+        if (valid) {
+            if (sh >= kGridBits) {
+                pos = (lane & 1) ? n : 0;
+            } else {
+                const Key base = morton3(cx, cy, cz) << (3 * sh);
+                const Key bound = (lane & 1) ? base + (Key(1) << (3 * sh)) : base;
+                pos = lower_bound_key(codes, n, bound);
+            }
+        }
+    }
+    const long long b = __shfl_sync(0xffffffffu, pos, (lane & 7) * 2);
+    const long long e = __shfl_sync(0xffffffffu, pos, (lane & 7) * 2 + 1);
+    int len = (int)(e - b);
+    // inclusive prefix over the 8 cells (lanes 0..7 hold distinct cells)
+    int pre = len;
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, pre, d, 8);
+        if ((lane & 7) >= d) pre += v;
+    }
+    if (lane < 8) {
+        s_begin[warp][lane] = b;
+        s_pre[warp][lane + 1] = pre;
+        if (lane == 0) s_pre[warp][0] = 0;
+    }
+    __syncwarp();
+    const int total = s_pre[warp][8];
+    int found = 0;
+    const int64_t out_base = FILL ? splits[q] : 0;
+    for (int t0 = 0; t0 < total; t0 += 32) {
+        const int t = t0 + lane;
+        bool hit = false;
+        unsigned long long key = 0;
+        if (t < total) {
+            int c = 0;
+#pragma unroll
+            for (int k = 1; k < 8; ++k) c += (t >= s_pre[warp][k]) ? 1 : 0;
+            const float4 p = __ldg(spts + s_begin[warp][c] + (t - s_pre[warp][c]));
+            const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            hit = d2 < r2;
+            key = ((unsigned long long)__float_as_uint(d2) << 32) | __float_as_uint(p.w);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (FILL && hit) out_keys[out_base + found + __popc(m & ((1u << lane) - 1))] = key;
+        found += __popc(m);
+    }
+    if (!FILL && lane == 0) counts[q] = found;
+}
+
+// Per-row rank sort of the (d2, index) keys; keys are unique within a row.
+__global__ void __launch_bounds__(256)
+row_sort_kernel(const unsigned long long* __restrict__ keys, const int64_t* __restrict__ splits, long long nq,
+                int32_t* __restrict__ out_idx, float* __restrict__ out_d2) {
+    const long long q = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const int64_t b = splits[q];
+    const int n = (int)(splits[q + 1] - b);
+    if (n <= 32) {
+        const unsigned long long mine = lane < n ? keys[b + lane] : ~0ULL;
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += __shfl_sync(0xffffffffu, mine, j) < mine ? 1 : 0;
+        if (lane < n) {
+            out_idx[b + rank] = (int32_t)(unsigned)mine;
+            out_d2[b + rank] = __uint_as_float((unsigned)(mine >> 32));
+        }
+    } else {
+        for (int i = lane; i < n; i += 32) {
+            const unsigned long long mine = keys[b + i];
+            int rank = 0;
+            for (int j = 0; j < n; ++j) rank += __ldg(keys + b + j) < mine ? 1 : 0;
+            out_idx[b + rank] = (int32_t)(unsigned)mine;
+            out_d2[b + rank] = __uint_as_float((unsigned)(mine >> 32));
+        }
+    }
+}
+
+// compat = (min(s_v, 2 r_p) / max(s_v, 2 r_p))^2   (nsearch.cpp:149-161)
+__global__ void __launch_bounds__(256)
+scale_compat_kernel(const float* __restrict__ sizes, const float* __restrict__ radii, const int32_t* __restrict__ idx,
+                    const int64_t* __restrict__ splits, long long nq, float* __restrict__ out) {
+    const long long q = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const float a = sizes[q];
+    const int64_t e = splits[q + 1];
+    for (int64_t j = splits[q] + lane; j < e; j += 32) {
+        const float b = 2.0f * __ldg(radii + idx[j]);
+        const float t = fminf(a, b) / fmaxf(a, b);
+        out[j] = __fmul_rn(t, t);
+    }
+}
+
+void search_prepare(Search& S, const float* d_points, int64_t n, const float* d_queries, const float* d_radii,
+                    int64_t nq, cudaStream_t s) {
+    S.n = n;
+    S.nq = nq;
+    S.queries = d_queries;
+    S.radii = d_radii;
+    // bounding cube of the points
+    DevBuf<unsigned> mm(6, s);
+    ASRB_CUDA(cudaMemsetAsync(mm.get(), 0xff, 3 * sizeof(unsigned), s));
+    ASRB_CUDA(cudaMemsetAsync(mm.get() + 3, 0, 3 * sizeof(unsigned), s));
+    unsigned h[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0, 0, 0};
+    if (n > 0) {
+        const unsigned blocks = (unsigned)std::min<size_t>(grid_for(n, 256), 148 * 8);
+        bbox_kernel<<<blocks, 256, 0, s>>>(d_points, n, mm.get(), mm.get() + 3);
+        ASRB_CHECK_LAUNCH();
+        ASRB_CUDA(cudaMemcpyAsync(h, mm.get(), sizeof(h), cudaMemcpyDeviceToHost, s));
+        ASRB_CUDA(cudaStreamSynchronize(s));
+    }
+    float edge = 0.f;
+    for (int a = 0; a < 3; ++a) {
+        const float lo = h[a] == 0xffffffffu ? 0.f : from_ordered_bits(h[a]);
+        const float hi = h[3 + a] == 0 ? 0.f : from_ordered_bits(h[3 + a]);
+        S.frame_origin[a] = lo;
+        edge = std::max(edge, hi - lo);
+    }
+    if (!(edge > 0.f)) edge = 1.f;
+    S.frame_inv_h = (float)(2097152.0 / ((double)edge * 1.000001));
+    BinFrame f{{S.frame_origin[0], S.frame_origin[1], S.frame_origin[2]}, S.frame_inv_h};
+
+    S.codes.alloc((size_t)n, s);
+    S.spts.alloc((size_t)n, s);
+    DevBuf<uint32_t> order((size_t)n, s);
+    if (n > 0) {
+        point_code_kernel<<<grid_for(n, 256), 256, 0, s>>>(d_points, n, f, S.codes.get(), order.get());
+        ASRB_CHECK_LAUNCH();
+        sort_pairs_u64_u32(S.codes.get(), order.get(), (size_t)n, s, 63);
+        gather_points_kernel<<<grid_for(n, 256), 256, 0, s>>>(d_points, order.get(), n, (float4*)S.spts.get());
+        ASRB_CHECK_LAUNCH();
+    }
+    // count pass
+    DevBuf<int32_t> counts((size_t)nq, s);
+    S.splits.alloc((size_t)nq + 1, s);
+    if (nq > 0) {
+        ball_query_kernel<false><<<grid_for(nq, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
+                S.codes.get(), (const float4*)S.spts.get(), n, f, d_queries, d_radii, nq, counts.get(), nullptr,
+                nullptr);
+        ASRB_CHECK_LAUNCH();
+    }
+    exclusive_sum_i32_to_i64(counts.get(), S.splits.get(), (size_t)nq, s);
+    S.num_pairs = d2h_scalar(S.splits.get() + nq, s);
+}
+
+void search_fill(Search& S, int32_t* d_idx, float* d_d2, int64_t* d_splits, cudaStream_t s) {
+    BinFrame f{{S.frame_origin[0], S.frame_origin[1], S.frame_origin[2]}, S.frame_inv_h};
+    ASRB_CUDA(cudaMemcpyAsync(d_splits, S.splits.get(), ((size_t)S.nq + 1) * sizeof(int64_t),
+                              cudaMemcpyDeviceToDevice, s));
+    if (S.nq == 0 || S.num_pairs == 0) return;
+    DevBuf<unsigned long long> keys((size_t)S.num_pairs, s);
+    ball_query_kernel<true><<<grid_for(S.nq, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
+            S.codes.get(), (const float4*)S.spts.get(), S.n, f, S.queries, S.radii, S.nq, nullptr, S.splits.get(),
+            keys.get());
+    ASRB_CHECK_LAUNCH();
+    row_sort_kernel<<<grid_for((size_t)S.nq * 32, 256), 256, 0, s>>>(keys.get(), S.splits.get(), S.nq, d_idx, d_d2);
+    ASRB_CHECK_LAUNCH();
+}
+
+void scale_compat(const float* d_sizes, const float* d_radii, const int32_t* d_idx, const int64_t* d_splits,
+                  int64_t nq, float* d_out, cudaStream_t s) {
+    if (nq == 0) return;
+    scale_compat_kernel<<<grid_for((size_t)nq * 32, 256), 256, 0, s>>>(d_sizes, d_radii, d_idx, d_splits, nq, d_out);
+    ASRB_CHECK_LAUNCH();
+}
+
+}  // namespace asrb

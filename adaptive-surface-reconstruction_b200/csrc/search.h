@@ -1,0 +1,27 @@
+#pragma once
+#include "common.cuh"
+
+namespace asrb {
+
+struct Float4Pod {
+    float x, y, z, w;
+};
+
+struct Search {
+    int64_t n = 0, nq = 0, num_pairs = 0;
+    const float* queries = nullptr;  // borrowed until search_fill
+    const float* radii = nullptr;
+    float frame_origin[3] = {0, 0, 0};
+    float frame_inv_h = 1.f;
+    DevBuf<Key> codes;       // sorted Morton codes of the points
+    DevBuf<Float4Pod> spts;  // points in sorted order, w = original index bits
+    DevBuf<int64_t> splits;  // [nq+1]
+};
+
+void search_prepare(Search& S, const float* d_points, int64_t n, const float* d_queries, const float* d_radii,
+                    int64_t nq, cudaStream_t s);
+void search_fill(Search& S, int32_t* d_idx, float* d_d2, int64_t* d_splits, cudaStream_t s);
+void scale_compat(const float* d_sizes, const float* d_radii, const int32_t* d_idx, const int64_t* d_splits,
+                  int64_t nq, float* d_out, cudaStream_t s);
+
+}  // namespace asrb

@@ -1,0 +1,36 @@
+#pragma once
+#include "common.cuh"
+
+namespace asrb {
+
+struct Int4Pod {
+    int x, y, z, w;
+};
+
+// Slot-sorted view of one neighbour table; reused by every convolution on it.
+struct ConvPlan {
+    int64_t V_out = 0, E = 0;
+    int K = 0;
+    int max_tiles = 0;
+    DevBuf<int32_t> p_in, p_out;  // [E] pairs sorted (stably) by kernel slot
+    DevBuf<uint32_t> perm;        // [E] original CSR position of each sorted pair
+    DevBuf<Int4Pod> tiles;        // (slot, first pair, count, -)
+    DevBuf<int> num_tiles;        // device scalar
+    DevBuf<int> slot_begin;       // [K+1]
+};
+
+void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, const int64_t* d_splits, int64_t V_out,
+                     int64_t E, int K, cudaStream_t s);
+
+// out must hold V_out*Cout floats.  imp_in (per input row, gathered through the
+// index) and/or imp_entry (per CSR entry) weight channels >= imp_col;
+// normalize divides channels >= norm_col by norm[row] (or the row length when
+// norm is null) where that is non-zero.
+void sparse_conv_forward(const ConvPlan& P, const float* x, const float* w, int Cin, int Cout, const float* imp_in,
+                         const float* imp_entry, int imp_col, int normalize, int norm_col, const float* norm,
+                         const int64_t* splits, const float* bias, int relu, float* out, cudaStream_t s);
+
+void row_importance(const float* imp, const int32_t* idx, const int64_t* splits, int64_t V, float* out,
+                    cudaStream_t s);
+
+}  // namespace asrb

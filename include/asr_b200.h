@@ -1,0 +1,173 @@
+/*
+ * asr_b200 — C ABI of the B200-native octree-conv -> SDF hot path.
+ *
+ * Drop-in boundary for the hot path of isl-org/adaptive-surface-reconstruction
+ * (SURVEY.md §8b).  The reference has no FFI for this path (its only C-linkage
+ * hook is the unused ASR_API_EXTERN_C macro, cpp/lib/asr_config.h:18-28); the
+ * entry points below are what a binding for the reference's own interfaces
+ * would call.  Each one cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer on the current CUDA device,
+ *     h_* is a HOST pointer; buffers are owned by the caller (PyTorch);
+ *   - variable-length results are two-phase: a *_count / *_create call returns the
+ *     sizes, the caller allocates, a *_fill / *_get call writes;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it.  A
+ *     call that returns a size synchronises that stream once;
+ *   - return value: 0 ok, 1 invalid argument (reference: std::invalid_argument ->
+ *     ValueError), 2 runtime error (std::runtime_error -> RuntimeError), 3 CUDA
+ *     error; asr_last_error() returns the thread-local message;
+ *   - there is NO CPU fallback: without a CUDA device every call fails with 3.
+ */
+#ifndef ASR_B200_H
+#define ASR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASR_B200_VERSION 100
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+int asr_version(void);
+const char* asr_last_error(void);
+/* number of kernels this library has launched since load (bench.py gpu_launches) */
+int64_t asr_kernel_launches(void);
+
+/* ---------------------------------------------------------------- octree
+ * replaces asr::CreateOctreeFromPoints, cpp/lib/octree.h:145 / octree.cpp:230-280
+ * (python: create_octree, cpp/pybind/module.cpp:372-374).  The handle mirrors the
+ * opaque `Octree` object of the python module (module.cpp:282). */
+typedef struct asr_octree asr_octree;
+
+int asr_octree_create(const float* d_points, const float* d_radii, int64_t num_points,
+                      const float h_bb_min[3], const float h_bb_max[3], float radius_scale,
+                      int grow_steps, int max_depth, void* stream, asr_octree** out);
+void asr_octree_destroy(asr_octree* tree);
+int64_t asr_octree_num_leaves(const asr_octree* tree);
+int64_t asr_octree_num_nodes(const asr_octree* tree);
+int asr_octree_balance_rounds(const asr_octree* tree);
+/* Octree::leaves (octree.h:127): sorted location codes, u64[num_leaves] */
+int asr_octree_get_leaves(const asr_octree* tree, uint64_t* d_out, void* stream);
+/* Octree::voxel_size / inv_voxel_size / offset (octree.h:120,131-132): host arrays [22],[22],[3] */
+int asr_octree_get_frame(const asr_octree* tree, float* h_voxel_size, float* h_inv_voxel_size,
+                         int32_t* h_offset);
+
+/* ---------------------------------------------------------------- grid hierarchy
+ * replaces asr::CreateGridsFromOctree, cpp/lib/grid.h:23 / grid.cpp:245-314
+ * (python: create_grids_from_octree, module.cpp:402-403).  Builds `num_levels`
+ * grids inside the handle; sizes per level are then queried and the arrays of
+ * ASRGrid (cpp/lib/asr_types.h:30-66) copied out.  Any output pointer may be NULL.
+ * voxel_* arrays exist on level 0, and on all levels iff voxel_info_all_levels;
+ * up_* arrays exist on every level but the last (up row splits are arange). */
+int asr_grids_build(asr_octree* tree, int num_levels, int voxel_info_all_levels, void* stream);
+int asr_grids_level_size(const asr_octree* tree, int level, int64_t* num_voxels, int64_t* num_neighbors);
+int asr_grids_get(const asr_octree* tree, int level, uint64_t* d_voxel_keys, float* d_voxel_centers,
+                  float* d_voxel_sizes, int32_t* d_neighbors_index, uint8_t* d_neighbors_kernel_index,
+                  int64_t* d_neighbors_row_splits, int32_t* d_up_neighbors_index,
+                  uint8_t* d_up_neighbors_kernel_index, int64_t* d_up_neighbors_row_splits, void* stream);
+
+/* ---------------------------------------------------------------- dual cells
+ * replaces asr::CreateDualVertexIndices, cpp/lib/grid.h:28 / grid.cpp:450-459
+ * (python: create_dual_vertex_indices, module.cpp:443): [num_duals, 8] leaf indices. */
+int asr_duals_count(asr_octree* tree, int64_t* num_duals, void* stream);
+int asr_duals_fill(asr_octree* tree, int64_t* d_dual_vertex_indices, void* stream);
+
+/* ---------------------------------------------------------------- aggregation neighbours
+ * replaces the Open3D MultiRadiusIndex/MultiRadiusSearch calls of
+ * asr::ComputeAggregationNeighborsAndScaleCompatibility, cpp/lib/nsearch.h:72-80 /
+ * nsearch.cpp:107-162 (python twin: o3d.core.nns multi_radius_search,
+ * models/v0/datareader.py:776-785): per query all points with d^2 < r^2, ascending
+ * by d^2 (ties by index); distances are SQUARED. */
+typedef struct asr_search asr_search;
+int asr_radius_search_create(const float* d_points, int64_t num_points, const float* d_queries,
+                             const float* d_radii, int64_t num_queries, void* stream, asr_search** out,
+                             int64_t* num_pairs);
+int asr_radius_search_fill(asr_search* search, int32_t* d_neighbors_index, float* d_neighbors_dist,
+                           int64_t* d_neighbors_row_splits, void* stream);
+void asr_radius_search_destroy(asr_search* search);
+/* (min(s_v, 2 r_p) / max(s_v, 2 r_p))^2 per pair, nsearch.cpp:149-161 / models/common.py:19-44 */
+int asr_scale_compatibility(const float* d_voxel_sizes, const float* d_point_radii, const int32_t* d_neighbors_index,
+                            const int64_t* d_neighbors_row_splits, int64_t num_queries, float* d_out, void* stream);
+/* scale_compat * clamp((1 - d2)^3, 0, 1), net_definitions_torch.py:107 + common_torch.py:21-22 */
+int asr_aggregation_importance(const float* d_scale_compat, const float* d_dist, int64_t num_pairs, float* d_out,
+                               void* stream);
+
+/* ---------------------------------------------------------------- continuous conv
+ * replaces open3d.ml.torch.ops.continuous_conv as configured by the reference
+ * (net_definitions_torch.py:53-70,108-116): ball_to_cube_radial, align_corners,
+ * linear interpolation.  filters [S,S,S,Cin,Cout]; extents [V] (stride 1) or [1]
+ * (stride 0); offset [3] or NULL; importance pointers may be NULL; bias may be
+ * NULL; relu != 0 fuses the layer activation. */
+int asr_continuous_conv(const float* d_filters, const float* d_out_positions, const float* d_extents,
+                        int extents_stride, const float* d_offset, const float* d_inp_positions,
+                        const float* d_inp_features, const float* d_inp_importance, const int32_t* d_neighbors_index,
+                        const float* d_neighbors_importance, const int64_t* d_neighbors_row_splits,
+                        int64_t num_out, int kernel_size, int in_channels, int out_channels, int normalize,
+                        const float* d_bias, int relu, float* d_out_features, void* stream);
+
+/* ---------------------------------------------------------------- generalized sparse conv
+ * replaces open3d.ml.torch.ops.sparse_conv + ops.reduce_subarrays_sum as used by
+ * SpecialSparseConv.forward, models/common_torch.py:95-148.  A plan is the
+ * slot-sorted form of one neighbour table (neighbors_index, neighbors_kernel_index,
+ * neighbors_row_splits) and is reused by every convolution on that table. */
+typedef struct asr_conv_plan asr_conv_plan;
+int asr_conv_plan_create(const int32_t* d_neighbors_index, const uint8_t* d_neighbors_kernel_index,
+                         const int64_t* d_neighbors_row_splits, int64_t num_out, int64_t num_entries,
+                         int kernel_size, void* stream, asr_conv_plan** out);
+void asr_conv_plan_destroy(asr_conv_plan* plan);
+/* out[o] = sum_n imp_n * x[idx_n] @ filters[slot_n]; channels >= importance_col are
+ * weighted by imp_n = d_inp_importance[idx_n] (and/or d_neighbors_importance[n]);
+ * normalize != 0 divides channels >= normalize_col by d_normalizer[o] (or by the row
+ * length when d_normalizer is NULL) where non-zero; then + bias, ReLU if requested.
+ * Channel counts must be multiples of 4; all float pointers 16-byte aligned. */
+int asr_sparse_conv(const asr_conv_plan* plan, const float* d_filters, const float* d_inp_features,
+                    int in_channels, int out_channels, const float* d_inp_importance,
+                    const float* d_neighbors_importance, int importance_col, int normalize, int normalize_col,
+                    const float* d_normalizer, const int64_t* d_neighbors_row_splits, const float* d_bias, int relu,
+                    float* d_out_features, void* stream);
+/* out[o] = sum_{n in row o} values[index ? index[n] : n]  (ops.reduce_subarrays_sum, common_torch.py:124-128) */
+int asr_reduce_subarrays_sum(const float* d_values, const int32_t* d_index, const int64_t* d_row_splits,
+                             int64_t num_rows, float* d_out, void* stream);
+/* ops.invert_neighbors_list, net_definitions_torch.py:30-35 */
+int asr_invert_neighbors_list(int64_t num_points, const int32_t* d_inp_neighbors_index,
+                              const int64_t* d_inp_neighbors_row_splits, int64_t num_queries, int64_t num_entries,
+                              const void* d_inp_attributes, int attribute_bytes, int32_t* d_neighbors_index,
+                              int64_t* d_neighbors_row_splits, void* d_neighbors_attributes, void* stream);
+
+/* ---------------------------------------------------------------- decoder MLP
+ * replaces UNet5.decode / decode_with_gradient, net_definitions_torch.py:655-686.
+ * weights in torch.nn.Linear layout: w1 [32,35], b1 [32], w2 [32,32], b2 [32], w3 [2,32].
+ * d_shifts may be NULL (zeros, as asr.cpp:324); d_signed_scale (may be NULL)
+ * multiplies channel 0 per voxel (asr.cpp:334-336); d_grad (may be NULL) receives
+ * d value[:,0] / d shift. */
+int asr_decode(const float* d_shifts, const float* d_code, int64_t num_voxels, const float* d_w1, const float* d_b1,
+               const float* d_w2, const float* d_b2, const float* d_w3, const float* d_signed_scale,
+               float* d_values, float* d_grad, void* stream);
+
+/* ---------------------------------------------------------------- dual contouring (vertices)
+ * replaces the vertex passes of asr::CreateTriangleMesh, cpp/lib/contouring.h:25-30 /
+ * contouring.cpp:66-199.  values [V,2] (signed, unsigned), dual indices [D,8],
+ * node positions [V,3].  _count fills d_flag[D] (u8) and d_offset[D+1] (i64) scratch
+ * owned by the caller and returns the number of vertices; _fill writes
+ * vertices [M,3] and (optionally) the dual index of every vertex [M]. */
+int asr_contour_count(const float* d_values, const int64_t* d_dual_indices, int64_t num_duals,
+                      float unsigned_threshold, uint8_t* d_flag, int64_t* d_offset, int64_t* num_vertices,
+                      void* stream);
+int asr_contour_fill(const float* d_values, const int64_t* d_dual_indices, int64_t num_duals,
+                     float unsigned_threshold, const float* d_node_positions, const uint8_t* d_flag,
+                     const int64_t* d_offset, float* d_vertices, int64_t* d_vertex_dual, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASR_B200_H */

@@ -74,7 +74,10 @@ class PortOctree:
 
     def __del__(self):
         if getattr(self, "h", None):
-            lib().og_octree_free(self.h)
+            try:
+                lib().og_octree_free(self.h)
+            except Exception:  # interpreter shutdown
+                pass
             self.h = None
 
     def leaves(self):

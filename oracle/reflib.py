@@ -96,7 +96,10 @@ class RefOctree:
 
     def __del__(self):
         if getattr(self, "h", None):
-            lib().ref_octree_free(self.h)
+            try:
+                lib().ref_octree_free(self.h)
+            except Exception:  # interpreter shutdown
+                pass
             self.h = None
 
     def leaves(self):

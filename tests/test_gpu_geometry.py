@@ -1,0 +1,128 @@
+"""GPU parity (bit-exact) of the octree / grid / dual-cell / contouring kernels
+against the geometry oracles, through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import dev, small_clouds, u64
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(c, **kw):
+    from asr_b200 import ops
+    return ops.Octree(dev(c["points"]), dev(c["radii"]), c["bb_min"], c["bb_max"], **kw)
+
+
+@pytest.mark.parametrize("name,cloud,levels", list(small_clouds()), ids=lambda x: x if isinstance(x, str) else None)
+def test_octree_grids_duals_bit_exact(name, cloud, levels, geom_checkers):
+    t = _build(cloud)
+    leaves = u64(t.leaves())
+    grids = t.grids(levels, True)
+    duals = t.dual_vertex_indices().cpu().numpy()
+    for cname, Cls in geom_checkers:
+        o = Cls(cloud["points"], cloud["radii"], cloud["bb_min"], cloud["bb_max"])
+        assert np.array_equal(leaves, o.leaves()), cname
+        assert t.num_nodes == len(o.nodes()), cname
+        for a, b in zip(t.frame(), o.params()):
+            assert np.array_equal(a, b), cname
+        og = o.grids(levels, True)
+        for l, (g, r) in enumerate(zip(grids, og)):
+            assert set(g) == set(r), (cname, l, set(g) ^ set(r))
+            for k, v in r.items():
+                mine = g[k].cpu().numpy()
+                if k == "voxel_keys":
+                    mine = mine.view(np.uint64)
+                assert mine.dtype == v.dtype and mine.shape == v.shape, (cname, l, k, mine.dtype, mine.shape, v.shape)
+                assert np.array_equal(mine, v), (cname, l, k)
+        od = o.dual_vertex_indices()
+        assert np.array_equal(duals.astype(np.uint64), od), cname
+
+
+def test_grids_without_voxel_info_and_depth_limit(geom_checkers):
+    from asr_b200 import clouds
+    c = clouds.adaptive_blob(20000, seed=4)
+    t = _build(c, max_depth=6)
+    grids = t.grids(3, False)
+    cname, Cls = geom_checkers[-1]
+    o = Cls(c["points"], c["radii"], c["bb_min"], c["bb_max"], max_depth=6)
+    og = o.grids(3, False)
+    for l, (g, r) in enumerate(zip(grids, og)):
+        assert set(g) == set(r), (l, set(g) ^ set(r))
+        for k, v in r.items():
+            mine = g[k].cpu().numpy()
+            if k == "voxel_keys":
+                mine = mine.view(np.uint64)
+            assert np.array_equal(mine, v), (l, k)
+
+
+def test_margin_free_bbox_reproduces_junk_leaves(geom_checkers):
+    """C++ driver bbox (asr.cpp:148-150): the extreme point maps to INVALID_KEY and
+    six junk level-0 leaves 2..7 appear."""
+    from asr_b200 import clouds
+    c = clouds.sphere(5000, seed=7)
+    c["bb_min"], c["bb_max"] = c["points"].min(0), c["points"].max(0)
+    t = _build(c)
+    leaves = u64(t.leaves())
+    cname, Cls = geom_checkers[-1]
+    o = Cls(c["points"], c["radii"], c["bb_min"], c["bb_max"])
+    assert np.array_equal(leaves, o.leaves())
+    assert list(leaves[:6]) == [2, 3, 4, 5, 6, 7]
+    g, r = t.grids(5, True), o.grids(5, True)
+    for l in range(5):
+        for k, v in r[l].items():
+            mine = g[l][k].cpu().numpy()
+            if k == "voxel_keys":
+                mine = mine.view(np.uint64)
+            assert np.array_equal(mine, v, equal_nan=True), (l, k)
+    assert np.array_equal(t.dual_vertex_indices().cpu().numpy().astype(np.uint64), o.dual_vertex_indices())
+
+
+def test_empty_and_tiny_inputs():
+    from asr_b200 import ops
+    z = torch.zeros((0, 3), device="cuda")
+    t = ops.Octree(z, torch.zeros(0, device="cuda"), [0, 0, 0], [1, 1, 1])
+    assert t.num_leaves == 0
+    g = t.grids(2, True)
+    assert len(g) == 2 and g[0]["neighbors_row_splits"].tolist() == [0]
+    assert t.dual_vertex_indices().shape == (0, 8)
+    # a single huge-radius point -> the root is the only leaf
+    t = ops.Octree(torch.tensor([[0.5, 0.5, 0.5]], device="cuda"), torch.tensor([10.0], device="cuda"),
+                   [0, 0, 0], [1, 1, 1])
+    assert u64(t.leaves()).tolist() == [1]
+    g = t.grids(2, True)
+    assert g[0]["neighbors_index"].tolist() == [0] and g[0]["neighbors_kernel_index"].tolist() == [0]
+    # points outside the box are dropped (octree.cpp:248-251)
+    t = ops.Octree(torch.tensor([[2.0, 0.5, 0.5]], device="cuda"), torch.tensor([0.1], device="cuda"),
+                   [0, 0, 0], [1, 1, 1])
+    assert t.num_leaves == 0
+    with pytest.raises(ValueError):
+        ops.Octree(torch.zeros((4, 2), device="cuda"), torch.zeros(4, device="cuda"), [0, 0, 0], [1, 1, 1])
+    with pytest.raises(ValueError):
+        ops.Octree(torch.zeros((4, 3), device="cuda"), torch.zeros(3, device="cuda"), [0, 0, 0], [1, 1, 1])
+
+
+@pytest.mark.parametrize("name,cloud,levels", list(small_clouds())[:3], ids=lambda x: x if isinstance(x, str) else None)
+def test_contour_vertices_bit_exact(name, cloud, levels, geom_checkers):
+    from asr_b200 import ops
+    from oracle import geomlib, reflib
+    t = _build(cloud)
+    g = t.grids(1, True)[0]
+    duals = t.dual_vertex_indices()
+    c = g["voxel_centers"].cpu().numpy()
+    s = g["voxel_sizes"].cpu().numpy()
+    rng = np.random.default_rng(5)
+    centre = c.mean(0)
+    rad = np.linalg.norm(c - centre, axis=1)
+    dist = rad - 0.9 * np.median(rad) + 0.05 * np.sin(9 * c[:, 0])
+    vals = np.stack([dist, np.abs(dist) / s * rng.uniform(0.5, 1.5, len(s))], 1).astype(np.float32)
+    vals[::97, 0] = 0.0  # exact zeros never count as a sign change
+    for thr in (1.0, 0.4):
+        v, vd = ops.contour_vertices(dev(vals), duals, g["voxel_centers"], thr)
+        pv, pd = geomlib.contour_vertices(vals, duals.cpu().numpy().astype(np.uint64), c, thr)
+        assert len(pv) > 20
+        assert np.array_equal(vd.cpu().numpy().astype(np.uint64), pd)
+        assert np.array_equal(v.cpu().numpy(), pv)
+        if reflib.available():
+            m = reflib.create_triangle_mesh(vals, duals.cpu().numpy().astype(np.uint64), c, thr)
+            assert np.array_equal(m["vertices"][:len(pv)], v.cpu().numpy())
