@@ -1,0 +1,110 @@
+"""The hot path end to end on one GPU: (points, normals, radii) -> octree -> grid
+hierarchy + neighbour tables -> dual cells -> aggregation neighbours ->
+aggregate / unet / decode -> dual-contouring vertices.
+
+Python re-statement of the *sequencing* in asr::ReconstructSurface (reference
+cpp/lib/asr.cpp:143-342); every stage is a kernel of libasr_b200.so.  The input
+dict has exactly the keys the reference builds (asr.cpp:159-312).
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+class StageTimer:
+    """CUDA-event timer per pipeline stage (enabled on demand; adds syncs)."""
+
+    def __init__(self, enabled=False):
+        self.enabled = enabled
+        self.ms = {}
+        self._t = None
+
+    def start(self):
+        if self.enabled:
+            torch.cuda.synchronize()
+            self._t = time.perf_counter()
+
+    def lap(self, name):
+        if self.enabled:
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            self.ms[name] = self.ms.get(name, 0.0) + (now - self._t) * 1e3
+            self._t = now
+
+
+def build_input_dict(points, normals, radii, bb_min, bb_max, levels=5, radius_scale=1.0, max_depth=21, timer=None):
+    """Grid building + aggregation search (asr.cpp:143-312).  Returns
+    (input_dict, dual_vertex_indices, octree)."""
+    timer = timer or StageTimer()
+    timer.start()
+    tree = ops.Octree(points, radii, bb_min, bb_max, radius_scale, 0, max_depth)
+    timer.lap("octree")
+    duals = tree.dual_vertex_indices()
+    timer.lap("duals")
+    grids = tree.grids(levels, True)
+    timer.lap("grids")
+    ones = torch.ones((points.shape[0], 1), dtype=torch.float32, device=points.device)
+    d = {"points": points, "feats": torch.cat([normals, ones], 1)}
+    for i, g in enumerate(grids):
+        for k, v in g.items():
+            if k != "voxel_keys":
+                d[k + str(i)] = v
+    if "voxel_centers0" not in d:  # empty tree
+        d["voxel_centers0"] = torch.zeros((0, 3), dtype=torch.float32, device=points.device)
+        d["voxel_sizes0"] = torch.zeros(0, dtype=torch.float32, device=points.device)
+    idx, dist, rs = ops.multi_radius_search(points, d["voxel_centers0"], d["voxel_sizes0"])
+    d["aggregation_neighbors_index"] = idx
+    d["aggregation_neighbors_dist"] = dist
+    d["aggregation_row_splits"] = rs
+    d["aggregation_scale_compat"] = ops.scale_compatibility(d["voxel_sizes0"], radii, idx, rs)
+    timer.lap("search")
+    return d, duals, tree
+
+
+def run_network(model, input_dict, timer=None):
+    """aggregate -> unet -> decode(shift = 0) with channel 0 rescaled by the voxel
+    size (asr.cpp:314-336).  Returns values [V0, 2]."""
+    timer = timer or StageTimer()
+    timer.start()
+    feats = model.aggregate(input_dict)
+    timer.lap("aggregate")
+    code = model.unet(feats, input_dict)
+    timer.lap("unet")
+    values = model.decode(None, code, signed_scale=input_dict["voxel_sizes0"])
+    timer.lap("decode")
+    return values
+
+
+def reconstruct_vertices(model, points, normals, radii, bb_min=None, bb_max=None, levels=None, radius_scale=1.0,
+                         max_depth=21, contouring_value_threshold=1.0, timer=None):
+    """Whole path on device tensors.  bb defaults to the exact min/max of the
+    points like the C++ driver (asr.cpp:148-150)."""
+    timer = timer or StageTimer()
+    levels = levels or model.octree_levels
+    if bb_min is None:
+        bb_min = points.min(0).values.cpu().numpy()
+        bb_max = points.max(0).values.cpu().numpy()
+    d, duals, tree = build_input_dict(points, normals, radii, bb_min, bb_max, levels, radius_scale, max_depth, timer)
+    values = run_network(model, d, timer)
+    timer.start()
+    verts, vdual = ops.contour_vertices(values, duals, d["voxel_centers0"], contouring_value_threshold)
+    timer.lap("contour")
+    return {"vertices": verts, "vertex_dual": vdual, "values": values, "dual_vertex_indices": duals,
+            "input_dict": d, "octree": tree}
+
+
+def reconstruct_vertices_host(model, points, normals, radii, bb_min=None, bb_max=None, **kw):
+    """Same path with HOST (numpy) buffers in and out: H2D of the cloud, the
+    device path, D2H of the vertices and SDF values.  This is the call the
+    `e2e` benchmark number times."""
+    dev = torch.device("cuda")
+    p = torch.from_numpy(np.ascontiguousarray(points, np.float32)).to(dev, non_blocking=True)
+    n = torch.from_numpy(np.ascontiguousarray(normals, np.float32)).to(dev, non_blocking=True)
+    r = torch.from_numpy(np.ascontiguousarray(radii, np.float32)).to(dev, non_blocking=True)
+    if bb_min is None:
+        bb_min, bb_max = points.min(0), points.max(0)
+    out = reconstruct_vertices(model, p, n, r, bb_min, bb_max, **kw)
+    return {"vertices": out["vertices"].cpu().numpy(), "values": out["values"].cpu().numpy()}
