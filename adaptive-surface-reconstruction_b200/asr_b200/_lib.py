@@ -22,6 +22,10 @@ SIGNATURES = {
     "asr_version": (_i32, []),
     "asr_last_error": (C.c_char_p, []),
     "asr_kernel_launches": (_i64, []),
+    "asr_profile_enable": (None, [_i32]),
+    "asr_profile_reset": (None, []),
+    "asr_profile_count": (_i32, []),
+    "asr_profile_get": (_i32, [_i32, C.c_char_p, _i32, C.POINTER(C.c_double), _pi64, C.POINTER(C.c_double)]),
     "asr_octree_create": (_i32, [_vp, _vp, _i64, _vp, _vp, _f32, _i32, _i32, _vp, _pp]),
     "asr_octree_destroy": (None, [_vp]),
     "asr_octree_num_leaves": (_i64, [_vp]),
@@ -85,3 +89,23 @@ def check(rc):
 
 def kernel_launches():
     return int(lib().asr_kernel_launches())
+
+
+def profile_enable(on=True):
+    lib().asr_profile_enable(int(bool(on)))
+
+
+def profile_reset():
+    lib().asr_profile_reset()
+
+
+def profile_read():
+    """{kernel name: {"ms": total device ms, "launches": n, "flops": algorithmic flops}}"""
+    L = lib()
+    out = {}
+    for i in range(L.asr_profile_count()):
+        name = C.create_string_buffer(64)
+        ms, fl, n = C.c_double(0), C.c_double(0), C.c_int64(0)
+        if L.asr_profile_get(i, name, 64, C.byref(ms), C.byref(n), C.byref(fl)) == 0:
+            out[name.value.decode()] = {"ms": ms.value, "launches": n.value, "flops": fl.value}
+    return out

@@ -208,6 +208,36 @@ def UNet5():
     return UNet(5)
 
 
+def seeded_weights(net, seed=0, scaled=True):
+    """Deterministic random weights for benchmarks/smoke runs (no checkpoint is
+    available offline).  scaled=False: the reference initialisers (kernels
+    U(-0.05, 0.05), zero biases, common_torch.py:57-58).  scaled=True:
+    fan-in-scaled kernels and small biases so activations stay O(1) through the
+    ~50 layers instead of decaying to zero."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            if name.endswith("offset"):
+                p.zero_()
+                continue
+            if name.endswith("kernel"):
+                if scaled:
+                    fan = p.shape[-2] * (7.7 if p.shape[0] == 55 else (16.0 if p.dim() == 5 else 1.0))
+                    lim = math.sqrt(6.0 / fan)
+                else:
+                    lim = 0.05
+            elif name.endswith("weight"):
+                lim = 1.0 / math.sqrt(p.shape[1])
+            else:  # biases
+                lim = (1.0 / math.sqrt(35.0) if name.startswith("dense") else (0.1 if scaled else 0.0))
+            p.copy_(((torch.rand(p.shape, generator=g, dtype=torch.float64) * 2 - 1) * lim).to(p.dtype))
+        for m in net.modules():
+            if isinstance(m, _Block):
+                m._fused = None
+    return net
+
+
 def from_state_dict(state_dict, levels=5, device="cuda"):
     net = UNet(levels)
     net.load_state_dict({k: torch.as_tensor(v) for k, v in state_dict.items()})

@@ -14,6 +14,10 @@ from ._lib import check, lib
 
 _i64 = C.c_int64
 
+# bench.py sets this to a list to collect the shape of every sparse conv of one
+# step (for the algorithmic byte / flop accounting); None = off.
+ACCOUNT = None
+
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -257,6 +261,9 @@ def sparse_conv(plan, filters, inp_features, inp_importance=None, neighbors_impo
         raise ValueError("filters.shape[0] does not match the plan's kernel size")
     if x.shape[1] != Cin:
         raise ValueError("inp_features channel count does not match the filter")
+    if ACCOUNT is not None:
+        ACCOUNT.append({"V_in": x.shape[0], "V_out": plan.num_out, "E": plan.idx.shape[0], "K": K, "Cin": Cin,
+                        "Cout": Cout, "importance": inp_importance is not None or neighbors_importance is not None})
     out = torch.empty((plan.num_out, Cout), dtype=torch.float32, device=x.device)
     check(lib().asr_sparse_conv(plan._h, _ptr(filters), _ptr(x), Cin, Cout,
                                 _ptr(_opt(inp_importance, torch.float32, "inp_importance")),

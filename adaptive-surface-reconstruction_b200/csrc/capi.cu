@@ -3,6 +3,7 @@
 #include "../../include/asr_b200.h"
 
 #include "internal.h"
+#include "profile.cuh"
 #include "search.h"
 #include "sparse_conv.h"
 
@@ -21,6 +22,10 @@ void contour_count(const float* values, const int64_t* duals, int64_t D, float t
                    int64_t* num_vertices, cudaStream_t s);
 void contour_fill(const float* values, const int64_t* duals, int64_t D, float thr, const float* pos,
                   const uint8_t* flag, const int64_t* offset, float* vertices, int64_t* vertex_dual, cudaStream_t s);
+void profile_set(bool on);
+void profile_reset();
+int profile_count();
+bool profile_get(int i, std::string& name, double& ms, long long& launches, double& flops);
 void invert_neighbors_list(int64_t num_points, const int32_t* idx, const int64_t* splits, int64_t Q, int64_t E,
                            const void* attrs, int attr_bytes, int32_t* out_idx, int64_t* out_splits, void* out_attrs,
                            cudaStream_t s);
@@ -75,6 +80,23 @@ extern "C" {
 int asr_version(void) { return ASR_B200_VERSION; }
 const char* asr_last_error(void) { return g_error.c_str(); }
 int64_t asr_kernel_launches(void) { return (int64_t)g_kernel_launches.load(); }
+
+void asr_profile_enable(int on) { profile_set(on != 0); }
+void asr_profile_reset(void) { profile_reset(); }
+int asr_profile_count(void) { return profile_count(); }
+int asr_profile_get(int i, char* name, int name_cap, double* total_ms, int64_t* launches, double* flops) {
+    std::string n;
+    double ms = 0, fl = 0;
+    long long l = 0;
+    if (!profile_get(i, n, ms, l, fl)) return 1;
+    if (name && name_cap > 0) {
+        snprintf(name, (size_t)name_cap, "%s", n.c_str());
+    }
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = l;
+    if (flops) *flops = fl;
+    return 0;
+}
 
 int asr_octree_create(const float* d_points, const float* d_radii, int64_t num_points, const float h_bb_min[3],
                       const float h_bb_max[3], float radius_scale, int grow_steps, int max_depth, void* stream,

@@ -11,6 +11,7 @@
 // shared-memory update), and contracts with the filter in registers
 // (lane = output channel).  Bias and ReLU of the layer are fused.
 #include "internal.h"
+#include "profile.cuh"
 
 namespace asrb {
 
@@ -96,6 +97,7 @@ void continuous_conv(const float* filters, const float* out_pos, const float* ex
     ASRB_REQUIRE(smem <= 200 * 1024, "continuous_conv: kernel_size^3 * in_channels too large for shared memory");
     if (smem > 48 * 1024)
         ASRB_CUDA(cudaFuncSetAttribute(cconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfileScope prof("continuous_conv", s, (double)V * 2.0 * S * S * S * Cin * Cout);
     cconv_kernel<<<grid_for(V, kCcWarps), kCcWarps * 32, smem, s>>>(filters, out_pos, extents, extents_stride, offset,
                                                                    inp_pos, inp_feat, inp_importance, nidx, nimp,
                                                                    splits, V, S, Cin, Cout, normalize, bias, relu, out);

@@ -9,6 +9,7 @@
 // flag -> scan -> compute, output order = dual order.
 #include "internal.h"
 #include "prims.cuh"
+#include "profile.cuh"
 
 namespace asrb {
 
@@ -72,6 +73,7 @@ contour_vertex_kernel(const float2* __restrict__ values, const int64_t* __restri
 void contour_count(const float* values, const int64_t* duals, int64_t D, float thr, uint8_t* flag, int64_t* offset,
                    int64_t* num_vertices, cudaStream_t s) {
     if (D) {
+        ProfileScope prof("contour_flag", s);
         contour_flag_kernel<<<grid_for(D, 256), 256, 0, s>>>((const float2*)values, duals, D, thr, flag);
         ASRB_CHECK_LAUNCH();
     }
@@ -82,6 +84,7 @@ void contour_count(const float* values, const int64_t* duals, int64_t D, float t
 void contour_fill(const float* values, const int64_t* duals, int64_t D, float thr, const float* pos,
                   const uint8_t* flag, const int64_t* offset, float* vertices, int64_t* vertex_dual, cudaStream_t s) {
     if (!D) return;
+    ProfileScope prof("contour_vertex", s);
     contour_vertex_kernel<<<grid_for(D, 256), 256, 0, s>>>((const float2*)values, duals, D, thr, pos, flag, offset,
                                                            vertices, vertex_dual);
     ASRB_CHECK_LAUNCH();

@@ -11,6 +11,7 @@
 // per-voxel rescaling of channel 0 that the pipeline applies before contouring
 // (cpp/lib/asr.cpp:334-336).
 #include "internal.h"
+#include "profile.cuh"
 
 namespace asrb {
 
@@ -82,6 +83,7 @@ void decode_mlp(const float* shifts, const float* code, int64_t V, const float* 
                 cudaStream_t s) {
     if (V == 0) return;
     const unsigned blocks = (unsigned)std::min<size_t>(grid_for((size_t)V * 32, 256), 148 * 8);
+    ProfileScope prof("decode_mlp", s, (double)V * 2.0 * (35 * 32 + 32 * 32 + 64));
     decode_kernel<<<blocks, 256, 0, s>>>(shifts, code, V, w1, b1, w2, b2, w3, signed_scale, values, grad);
     ASRB_CHECK_LAUNCH();
 }

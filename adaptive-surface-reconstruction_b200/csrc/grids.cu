@@ -9,6 +9,7 @@
 // scan over popcounts gives the CSR offsets (count -> scan -> fill).
 #include "internal.h"
 #include "prims.cuh"
+#include "profile.cuh"
 
 namespace asrb {
 
@@ -180,6 +181,7 @@ static void build_adjacency(GridLevel& g, cudaStream_t s) {
     DevBuf<unsigned long long> mask((size_t)V, s);
     DevBuf<int32_t> count((size_t)V, s);
     if (V) {
+        ProfileScope prof("adjacency_mask", s);
         adjacency_mask_kernel<<<grid_for((size_t)V * 32, 256), 256, 0, s>>>(g.keys.get(), V, mask.get(), count.get());
         ASRB_CHECK_LAUNCH();
     }
@@ -188,6 +190,7 @@ static void build_adjacency(GridLevel& g, cudaStream_t s) {
     g.nidx.alloc((size_t)g.E, s);
     g.nslot.alloc((size_t)g.E, s);
     if (V) {
+        ProfileScope prof("adjacency_fill", s);
         adjacency_fill_kernel<<<grid_for((size_t)V * 32, 256), 256, 0, s>>>(g.keys.get(), V, mask.get(),
                                                                             g.nsplits.get(), g.nidx.get(),
                                                                             g.nslot.get());
@@ -342,6 +345,7 @@ void duals_count(Octree& t, cudaStream_t s) {
     t.dual_offset.alloc((size_t)V + 1, s);
     DevBuf<uint8_t> count((size_t)V, s);
     if (V) {
+        ProfileScope prof("dual_flag", s);
         dual_flag_kernel<<<grid_for((size_t)V * 8, 256), 256, 0, s>>>(t.leaves.get(), V, t.groups.get(), t.num_groups,
                                                                       t.root_separate, t.node_leaf.get(),
                                                                       t.dual_mask.get(), count.get());
@@ -357,6 +361,7 @@ void duals_fill(Octree& t, int64_t* d_out, cudaStream_t s) {
     if (!V || !t.num_duals) return;
     DevBuf<int> err(1, s);
     ASRB_CUDA(cudaMemsetAsync(err.get(), 0, sizeof(int), s));
+    ProfileScope prof("dual_fill", s);
     dual_fill_kernel<<<grid_for((size_t)V * 8, 256), 256, 0, s>>>(t.leaves.get(), V, t.groups.get(), t.num_groups,
                                                                   t.root_separate, t.node_leaf.get(),
                                                                   t.node_rank.get(), t.dual_mask.get(),

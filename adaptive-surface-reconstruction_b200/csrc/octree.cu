@@ -17,6 +17,7 @@
 // Results are bit-identical to the reference (tests/test_geometry_parity.py).
 #include "internal.h"
 #include "prims.cuh"
+#include "profile.cuh"
 
 #include <algorithm>
 #include <cmath>

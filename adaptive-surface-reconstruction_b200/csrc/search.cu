@@ -19,6 +19,7 @@
 // strict `<` test resolves boundary points identically.
 #include "internal.h"
 #include "prims.cuh"
+#include "profile.cuh"
 #include "search.h"
 
 namespace asrb {
@@ -262,6 +263,7 @@ void search_prepare(Search& S, const float* d_points, int64_t n, const float* d_
     S.spts.alloc((size_t)n, s);
     DevBuf<uint32_t> order((size_t)n, s);
     if (n > 0) {
+        ProfileScope prof("search_point_sort", s);
         point_code_kernel<<<grid_for(n, 256), 256, 0, s>>>(d_points, n, f, S.codes.get(), order.get());
         ASRB_CHECK_LAUNCH();
         sort_pairs_u64_u32(S.codes.get(), order.get(), (size_t)n, s, 63);
@@ -272,6 +274,7 @@ void search_prepare(Search& S, const float* d_points, int64_t n, const float* d_
     DevBuf<int32_t> counts((size_t)nq, s);
     S.splits.alloc((size_t)nq + 1, s);
     if (nq > 0) {
+        ProfileScope prof("ball_query_count", s);
         ball_query_kernel<false><<<grid_for(nq, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
                 S.codes.get(), (const float4*)S.spts.get(), n, f, d_queries, d_radii, nq, counts.get(), nullptr,
                 nullptr);
@@ -287,6 +290,7 @@ void search_fill(Search& S, int32_t* d_idx, float* d_d2, int64_t* d_splits, cuda
                               cudaMemcpyDeviceToDevice, s));
     if (S.nq == 0 || S.num_pairs == 0) return;
     DevBuf<unsigned long long> keys((size_t)S.num_pairs, s);
+    ProfileScope prof("ball_query_fill_sort", s);
     ball_query_kernel<true><<<grid_for(S.nq, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
             S.codes.get(), (const float4*)S.spts.get(), S.n, f, S.queries, S.radii, S.nq, nullptr, S.splits.get(),
             keys.get());

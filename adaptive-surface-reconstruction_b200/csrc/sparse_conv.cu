@@ -32,6 +32,7 @@
 // convolution whose trailing `Cout - imp_col` channels carry the importance.
 #include "internal.h"
 #include "prims.cuh"
+#include "profile.cuh"
 #include "sparse_conv.h"
 
 namespace asrb {
@@ -120,6 +121,7 @@ void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, c
     P.tiles.alloc((size_t)P.max_tiles, s);
     P.num_tiles.alloc(1, s);
     P.slot_begin.alloc((size_t)K + 1, s);
+    ProfileScope prof("conv_plan_build", s);
     DevBuf<uint32_t> rows((size_t)E, s);
     DevBuf<uint8_t> keys((size_t)E, s);
     if (E) {
@@ -383,6 +385,7 @@ static void launch_tiles(const ConvPlan& P, const TileArgs& a, cudaStream_t s) {
         configured = true;
     }
     dim3 grid((unsigned)P.max_tiles, (unsigned)((a.Cout + TN - 1) / TN));
+    ProfileScope prof("sparse_conv_tile", s, 2.0 * (double)P.E * a.Cin * a.Cout);
     sparse_conv_tile_kernel<TN><<<grid, kThreads, smem, s>>>(a);
     ASRB_CHECK_LAUNCH();
 }
@@ -392,7 +395,10 @@ void sparse_conv_forward(const ConvPlan& P, const float* x, const float* w, int 
                          const int64_t* splits, const float* bias, int relu, float* out, cudaStream_t s) {
     ASRB_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0, "sparse_conv: channel counts must be multiples of 4");
     if (P.V_out == 0) return;
-    ASRB_CUDA(cudaMemsetAsync(out, 0, (size_t)P.V_out * Cout * sizeof(float), s));
+    {
+        ProfileScope prof("sparse_conv_zero", s);
+        ASRB_CUDA(cudaMemsetAsync(out, 0, (size_t)P.V_out * Cout * sizeof(float), s));
+    }
     if (P.E > 0) {
         TileArgs a;
         a.x = x;
@@ -413,6 +419,7 @@ void sparse_conv_forward(const ConvPlan& P, const float* x, const float* w, int 
         else launch_tiles<32>(P, a, s);
     }
     if (normalize || bias || relu) {
+        ProfileScope prof("sparse_conv_epilogue", s);
         conv_epilogue_kernel<<<grid_for((size_t)P.V_out * (Cout / 4), 256), 256, 0, s>>>(
                 out, P.V_out, Cout, normalize, norm_col, norm, splits, bias, relu);
         ASRB_CHECK_LAUNCH();

@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the octree-conv -> SDF hot path (BASELINE.json metric:
+"points/sec through octree-conv->SDF eval (10M pts, 6 levels)").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one pass of the whole path over one synthetic cloud: octree build
+from (points, radii) -> grid hierarchy + neighbour tables -> dual cells ->
+aggregation search -> aggregate / unet / decode -> dual-contouring vertices
+(stages a2..a14).  `value` times it with the cloud resident in
+HBM; `e2e` times the same call with HOST buffers (pinned H2D of the cloud,
+D2H of SDF values and vertices inside the timed region).
+
+`--impl reference` times the CPU path (reference geometry TUs from oracle/_ref +
+the torch-CPU restatement of the Open3D ops, all host threads) on a bounded
+sample of the same workload.  The oracle is used ONLY there and in the
+`cpu_baseline` leg; the GPU arm never touches it.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "adaptive-surface-reconstruction_b200"))
+
+METRIC = "points/sec through octree-conv->SDF eval (10M pts, 6 levels)"
+UNIT = "points/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def workload_name(args):
+    return "%s %.3gM pts, %d grid levels, full v0 U-Net (seeded random weights), fp32" % (
+        args.workload, args.points / 1e6, args.levels)
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            out.update({"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                        "samples": len(sm)})
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------ byte / flop model
+def algorithmic_bytes(sizes, convs):
+    """Compulsory HBM traffic per stage: every input read once,
+    every output written once.  sizes: N, V[l], E[l], P, D, M."""
+    N, V, E, P, D, M = sizes["N"], sizes["V"], sizes["E"], sizes["P"], sizes["D"], sizes["M"]
+    b = {}
+    b["octree_keys"] = 16 * N + 8 * V[0]
+    b["neighbor_tables"] = sum(8 * v + 5 * e + 8 * (v + 1) for v, e in zip(V, E)) + sum(21 * v for v in V[:-1])
+    b["duals"] = 8 * V[0] + 64 * D
+    b["search"] = 12 * N + 16 * V[0] + 12 * P + 8 * (V[0] + 1)
+    b["continuous_conv"] = 12 * P + 8 * (V[0] + 1) + 28 * N + 16 * V[0] + 128 * V[0] + 4 * P
+    conv = 0
+    for c in convs:
+        conv += 4 * c["V_in"] * c["Cin"] + 4 * c["V_out"] * c["Cout"] + 5 * c["E"] + 8 * (c["V_out"] + 1) + \
+            4 * c["K"] * c["Cin"] * c["Cout"] + (4 * c["V_in"] + 4 * c["V_out"] if c["importance"] else 0)
+    b["sparse_conv_stack"] = conv
+    b["decode"] = 128 * V[0] + 8 * V[0]
+    b["contour"] = 64 * D + 20 * V[0] + 12 * M
+    return b
+
+
+# ------------------------------------------------------------------------------------ CPU legs
+def cpu_pipeline_points_per_s(args, n_points, steps=1, warmup=0):
+    """The oracle CPU path on `n_points` of the same workload, all host threads."""
+    import torch
+    from asr_b200 import clouds
+    from oracle import model_cpu, pipeline_cpu
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cloud = clouds.make(args.workload, n_points, seed=args.seed)
+    P = model_cpu.init_params(args.levels, seed=0, stress=True)
+    times = {}
+    for _ in range(warmup):
+        pipeline_cpu.run(cloud, P, args.levels)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        times = {}
+        out = pipeline_cpu.run(cloud, P, args.levels, times=times)
+    dt = (time.perf_counter() - t0) / steps
+    geom = times.get("geometry", "port")
+    stage = {k: round(v, 4) for k, v in times.items() if k != "geometry"}
+    sample = ("%s cloud of %d points (same generator/seed), %d levels; geometry stages = %s (1 thread), search = scipy "
+              "cKDTree (all cores), network = torch-CPU restatement of the Open3D ops (%d threads); stage seconds %s"
+              % (args.workload, n_points, args.levels,
+                 "reference cpp/lib TUs (oracle/_ref)" if geom == "reference" else "oracle port", cores,
+                 json.dumps(stage)))
+    return n_points / dt, dt, cores, sample, int(out["values"].shape[0])
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    v, dt, cores, sample, v0 = cpu_pipeline_points_per_s(args, args.cpu_points, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "bounded_sample_points": args.cpu_points},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from asr_b200 import _lib, clouds, model, ops, pipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the GPU arm has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    _lib.lib()
+    peaks = load_peaks()
+
+    # replicas: every rank processes its own cloud of the named shape (weak scaling)
+    cloud = clouds.make(args.workload, args.points, seed=args.seed + rank)
+    net = model.seeded_weights(model.UNet(args.levels), seed=0).cuda()
+    host = {k: torch.from_numpy(cloud[k]).pin_memory() for k in ("points", "normals", "radii")}
+    devt = {k: v.cuda() for k, v in host.items()}
+    bb = (cloud["bb_min"], cloud["bb_max"])
+
+    def step_device():
+        return pipeline.reconstruct_vertices(net, devt["points"], devt["normals"], devt["radii"], bb[0], bb[1])
+
+    def step_host():
+        p = host["points"].cuda(non_blocking=True)
+        n = host["normals"].cuda(non_blocking=True)
+        r = host["radii"].cuda(non_blocking=True)
+        out = pipeline.reconstruct_vertices(net, p, n, r, bb[0], bb[1])
+        v = out["vertices"].cpu()
+        s = out["values"].cpu()
+        return out, v, s
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # one accounted + stage-timed step (untimed) for sizes and the byte model
+    ops.ACCOUNT = []
+    tm = pipeline.StageTimer(enabled=True)
+    out = pipeline.reconstruct_vertices(net, devt["points"], devt["normals"], devt["radii"], bb[0], bb[1], timer=tm)
+    convs, ops.ACCOUNT = ops.ACCOUNT, None
+    d = out["input_dict"]
+    sizes = {"N": args.points,
+             "V": [int(d["neighbors_row_splits%d" % i].shape[0] - 1) for i in range(args.levels)],
+             "E": [int(d["neighbors_index%d" % i].shape[0]) for i in range(args.levels)],
+             "P": int(d["aggregation_neighbors_index"].shape[0]), "D": int(out["dual_vertex_indices"].shape[0]),
+             "M": int(out["vertices"].shape[0])}
+    stage_ms = {k: round(v, 3) for k, v in tm.ms.items()}
+    del out, d
+    for _ in range(max(args.warmup - 1, 0)):
+        step_device()
+
+    # ---- device-resident timing (value) with the kernel profiler on
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    _lib.profile_reset()
+    _lib.profile_enable(True)
+    launches0 = _lib.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    launches = (_lib.kernel_launches() - launches0) // max(args.steps, 1)
+    _lib.profile_enable(False)
+    prof = _lib.profile_read()
+    clocks = sampler.stop()
+
+    # ---- end-to-end timing from pinned host buffers (e2e)
+    if not args.profile_run:
+        step_host()
+    barrier()
+    e0.record()
+    for _ in range(1 if args.profile_run else args.steps):
+        o, v, s = step_host()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    h2d = sum(t.numel() * t.element_size() for t in host.values())
+    d2h = v.numel() * 4 + s.numel() * 4
+
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = t.tolist()
+    ms_step, ms_step_e2e = ms_dev / args.steps, ms_e2e / args.steps
+    value = world * args.points / (ms_step * 1e-3)
+    e2e_value = world * args.points / (ms_step_e2e * 1e-3)
+
+    if rank == 0:
+        bytes_by_stage = algorithmic_bytes(sizes, convs)
+        total_bytes = sum(bytes_by_stage.values())
+        total_flops = sum(2.0 * c["E"] * c["Cin"] * c["Cout"] for c in convs)
+        kern = prof.get("sparse_conv_tile", {"ms": 0.0, "launches": 0, "flops": 0.0})
+        avg_ms = kern["ms"] / max(kern["launches"], 1)
+        flops_per_launch = kern["flops"] / max(kern["launches"], 1)
+        achieved = (kern["flops"] / (kern["ms"] * 1e-3) / 1e12) if kern["ms"] > 0 else 0.0
+        peak = peaks["bf16_tflops_sustained"]
+        roofline = {
+            "bound": "tensor", "kernel": "sparse_conv_tile_kernel", "achieved": achieved, "peak": peak,
+            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": "%s bf16 dense, sustained (kernel timed inside a long step)" % peaks["source"],
+            "note": "fp32 SIMT contraction today; the tensor-pipe peak is the bound this kernel is judged against",
+            "launches_per_step": kern["launches"] // max(args.steps, 1), "avg_launch_ms": avg_ms,
+            "algorithmic_flops_per_launch": flops_per_launch,
+            "share_of_step": kern["ms"] / max(ms_dev, 1e-9),
+            "algorithmic_gbs": bytes_by_stage["sparse_conv_stack"] * args.steps / max(kern["ms"] * 1e-3, 1e-12) / 1e9,
+        }
+        path = {
+            "algorithmic_bytes_per_point": total_bytes / args.points,
+            "algorithmic_flops_per_point": total_flops / args.points,
+            "hbm_roofline_ms": total_bytes / (peaks["hbm_gbs"] * 1e9) * 1e3,
+            "hbm_roofline_frac": total_bytes / (peaks["hbm_gbs"] * 1e9) * 1e3 / ms_step,
+            "bytes_by_stage": bytes_by_stage,
+        }
+        kernels = {k: {"ms_per_step": round(v["ms"] / args.steps, 4), "launches_per_step": v["launches"] // args.steps}
+                   for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "parallelism": "replicas x%d" % world if world > 1 else "1 gpu",
+                       "l2_policy": "inputs and every intermediate tensor larger than the 126 MB L2",
+                       "sizes": sizes},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_step_e2e},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "path_roofline": path,
+            "stage_ms_synchronised_untimed_step": stage_ms, "kernel_ms": kernels,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, dt, cores, sample, _ = cpu_pipeline_points_per_s(args, args.cpu_points)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="thingi_like")
+    ap.add_argument("--points", type=int, default=10_000_000)
+    ap.add_argument("--levels", type=int, default=6)
+    ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--cpu-points", type=int, default=200_000, help="bounded sample for the CPU legs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-run", action="store_true",
+                    help="for runs under ncu: no minimum warm-up, no e2e leg; the printed numbers are NOT bench values")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours" and not args.profile_run:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

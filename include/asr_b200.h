@@ -39,6 +39,14 @@ const char* asr_last_error(void);
 /* number of kernels this library has launched since load (bench.py gpu_launches) */
 int64_t asr_kernel_launches(void);
 
+/* Per-kernel device timing (CUDA events on the launching stream) for bench.py's
+ * roofline figures: enable, run, then read (name, total ms, launches, algorithmic
+ * flops) per instrumented kernel.  Reading synchronises the recorded events. */
+void asr_profile_enable(int on);
+void asr_profile_reset(void);
+int asr_profile_count(void);
+int asr_profile_get(int i, char* name, int name_cap, double* total_ms, int64_t* launches, double* flops);
+
 /* ---------------------------------------------------------------- octree
  * replaces asr::CreateOctreeFromPoints, cpp/lib/octree.h:145 / octree.cpp:230-280
  * (python: create_octree, cpp/pybind/module.cpp:372-374).  The handle mirrors the
