@@ -1,0 +1,154 @@
+"""Drop-in for the reference's python module `adaptivesurfacereconstruction`
+(pybind11 module asrpybind, cpp/pybind/module.cpp:279-489, re-exported by
+python/adaptivesurfacereconstruction/__init__.py:16-18) on the asr_b200 CUDA
+backend.  Same function names, keyword names, defaults, array dtypes/shapes and
+exception types; arrays go in and out as numpy (host) buffers exactly like the
+reference, the work happens on the current CUDA device.
+
+In scope (hot path): create_octree, create_grids_from_octree,
+create_dual_vertex_indices, reconstruct_surface (octree-conv -> SDF -> vertices).
+Rows §8 marks "next" and that are not built yet raise NotImplementedError instead
+of silently running elsewhere: KDTree (f-2), remove_connected_components (f-3),
+triangle connectivity of reconstruct_surface (f-1, returned empty with a warning).
+"""
+import os
+import warnings
+
+import numpy as np
+import torch
+
+from asr_b200 import model as _model
+from asr_b200 import ops as _ops
+from asr_b200 import pipeline as _pipeline
+
+__version__ = "0.2.0"
+INT64_MAX = np.iinfo(np.int64).max
+
+
+def get_version_str():
+    """module.cpp:284 — the reference returns ASR_VERSION."""
+    return __version__ + "+b200"
+
+
+def get_third_party_notices():
+    """module.cpp:287."""
+    return "asr_b200 uses PyTorch (BSD-3-Clause) and NVIDIA CUB (Apache-2.0 with LLVM exception)."
+
+
+class Octree:
+    """Opaque handle, no python methods (module.cpp:282)."""
+
+    def __init__(self, impl):
+        self._impl = impl
+
+
+def _f32(a, name, shape_msg, ndim, last=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)  # py::array::c_style | forcecast
+    if a.ndim != ndim or (last is not None and a.shape[-1] != last):
+        raise ValueError(shape_msg)
+    return a
+
+
+def create_octree(points, radii, bb_min, bb_max, radius_scale=1, grow_steps=0, max_depth=21):
+    """module.cpp:372-374 / pyCreateOctreeFromPoints :144-161."""
+    points = _f32(points, "points", "points must have shape [N,3]", 2, 3)
+    radii = np.ascontiguousarray(radii, dtype=np.float32)
+    if radii.ndim != 1 or radii.shape[0] != points.shape[0]:
+        raise ValueError("radii must have shape [N]")
+    t = _ops.Octree(torch.from_numpy(points).cuda(), torch.from_numpy(radii).cuda(), bb_min, bb_max,
+                    float(radius_scale), int(grow_steps), int(max_depth))
+    return Octree(t)
+
+
+def create_grids_from_octree(tree, num_levels, voxel_info_all_levels=False):
+    """module.cpp:402-403 / pyCreateGridsFromOctree :163-228: list (finest first)
+    of dicts of numpy arrays; a key is omitted when its array is empty."""
+    grids = tree._impl.grids(int(num_levels), bool(voxel_info_all_levels))
+    out = []
+    for g in grids:
+        d = {}
+        for k, v in g.items():
+            a = v.cpu().numpy()
+            d[k] = a.view(np.uint64) if k == "voxel_keys" else a
+        out.append(d)
+    return out
+
+
+def create_dual_vertex_indices(tree):
+    """module.cpp:443 / :230-235: size_t[num_duals, 8]."""
+    return tree._impl.dual_vertex_indices().cpu().numpy().view(np.uint64)
+
+
+_MODEL_CACHE = {}
+
+
+def _load_model(levels=5):
+    """The reference loads `model.pt` from the resource dir (asr.cpp:50,138-141:
+    env ASR_RESOURCE_DIR or <module dir>/asr_resources).  Accepts a TorchScript
+    archive or a plain state_dict file with the reference's key names."""
+    res = os.environ.get("ASR_RESOURCE_DIR", os.path.join(os.path.dirname(__file__), "asr_resources"))
+    path = os.path.join(res, "model.pt")
+    if path in _MODEL_CACHE:
+        return _MODEL_CACHE[path]
+    if not os.path.exists(path):
+        raise RuntimeError("model.pt not found in the resource dir %r (set ASR_RESOURCE_DIR); the released weights "
+                           "are not redistributable offline" % res)
+    try:
+        sd = torch.jit.load(path, map_location="cpu").state_dict()
+    except Exception:
+        sd = torch.load(path, map_location="cpu")
+    sd = {k: v for k, v in sd.items() if not k.startswith("_")}
+    net = _model.from_state_dict(sd, levels)
+    _MODEL_CACHE[path] = net
+    return net
+
+
+def reconstruct_surface(points, normals, radii, point_radius_scale=1.0, density_percentile_threshold=10.0,
+                        point_radius_estimation_knn=24, octree_max_depth=21, contouring_value_threshold=1.0,
+                        keep_n_connected_components=INT64_MAX, minimum_component_size=3, model=None):
+    """module.cpp:291-306 / pyReconstructSurface :58-109 -> asr::ReconstructSurface
+    (asr.cpp:95-349).  Runs the hot path (grid building, aggregation search,
+    aggregate/unet/decode, dual-contouring vertices) on the GPU.
+
+    Not built yet (SURVEY.md §8f "next" rows): the kNN radius estimation / density
+    pre-filter (radii must be given; density_percentile_threshold is ignored) and
+    the triangle connectivity (returned empty) / connected-component filter.
+    `model` (an asr_b200.model.UNet) overrides the model.pt lookup."""
+    points = _f32(points, "points", "points must have shape [num_points,3]", 2, 3)
+    normals = np.ascontiguousarray(normals, dtype=np.float32)
+    if normals.ndim != 2 or normals.shape != points.shape:
+        raise ValueError("normals must have shape [num_points,3]")
+    radii = np.ascontiguousarray(radii if radii is not None else [], dtype=np.float32)
+    if radii.size > 0 and (radii.ndim != 1 or radii.shape[0] != points.shape[0]):
+        raise ValueError("radii must have shape [num_point3]")
+    if points.shape[0] == 0:
+        raise RuntimeError("points is null!\n")
+    if radii.size == 0:
+        raise NotImplementedError("radius estimation (KDTree.compute_k_radius, SURVEY.md §8f-2) is not built yet: "
+                                  "pass per-point radii")
+    net = model if model is not None else _load_model()
+    out = _pipeline.reconstruct_vertices_host(net, points, normals, radii, radius_scale=float(point_radius_scale),
+                                              max_depth=int(octree_max_depth),
+                                              contouring_value_threshold=float(contouring_value_threshold))
+    warnings.warn("asr_b200.reconstruct_surface: triangle extraction (SURVEY.md §8f-1) is not built yet; "
+                  "'triangles' is empty", RuntimeWarning)
+    return {"vertices": out["vertices"], "triangles": np.zeros((0, 3), np.int32)}
+
+
+def remove_connected_components(vertices, triangles, keep_n_largest_components, minimum_component_size=3):
+    """module.cpp:348-350 — post-process row f-3, outside the hot path."""
+    vertices = _f32(vertices, "vertices", "vertices must have shape [N,3]", 2, 3)
+    triangles = np.ascontiguousarray(triangles, dtype=np.int32)
+    if triangles.ndim != 2 or triangles.shape[1] != 3:
+        raise ValueError("triangles must have shape [N,3]")
+    raise NotImplementedError("remove_connected_components (SURVEY.md §8f-3) is not built yet")
+
+
+class KDTree:
+    """module.cpp:455-489 — pre-filter row f-2, outside the hot path."""
+
+    def __init__(self, points):
+        points = np.asarray(points)
+        if points.ndim != 2 or points.shape[1] != 3:
+            raise ValueError("points must have shape [N,3]")
+        raise NotImplementedError("KDTree (SURVEY.md §8f-2) is not built yet")

@@ -1,0 +1,131 @@
+"""CPU: the C-ABI library loads and exports every symbol include/asr_b200.h
+declares (no compute without a GPU), the ctypes table mirrors the header, the
+product fails loudly without CUDA, and the host-side logic behaves."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "asr_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(asr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from asr_b200 import _lib
+    names = _declared()
+    assert len(names) >= 30
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), "libasr_b200.so does not export " + n
+    assert sorted(_lib.SIGNATURES) == names  # the ctypes table mirrors the header one to one
+    assert _lib.lib().asr_version() == 100
+
+
+def test_every_declaration_cites_the_reference():
+    src = open(HEADER).read()
+    for anchor in ("octree.cpp:230", "grid.cpp:245", "grid.cpp:450", "nsearch.cpp:107", "common_torch.py:95",
+                   "net_definitions_torch.py:655", "contouring.cpp:66", "module.cpp:372"):
+        assert anchor in src, anchor
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    from asr_b200 import _lib, ops
+    L = _lib.lib()
+    h = ctypes.c_void_p(0)
+    bb = (ctypes.c_float * 3)(0, 0, 0)
+    rc = L.asr_octree_create(None, None, 0, bb, bb, 1.0, 0, 21, None, ctypes.byref(h))
+    assert rc == 3 and b"no CUDA device" in L.asr_last_error()
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        ops.multi_radius_search(torch.zeros(3, 3), torch.zeros(1, 3), torch.ones(1))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        import open3d.ml.torch as ml3d
+        ml3d.ops.reduce_subarrays_sum(torch.zeros(3), torch.tensor([0, 3]))
+    # the product package never imports the oracle
+    r = subprocess.run([sys.executable, "-c",
+                        "import sys; sys.path[:0]=[%r, %r]; import asr_b200, asr_b200.model, asr_b200.pipeline, "
+                        "adaptivesurfacereconstruction, open3d.ml.torch; "
+                        "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules); print('clean')"
+                        % (ROOT, os.path.join(ROOT, "adaptive-surface-reconstruction_b200"))],
+                       capture_output=True, text=True)
+    assert "clean" in r.stdout, r.stderr[-1500:]
+
+
+def test_python_module_signatures_and_errors():
+    """Same names / keyword defaults / exception types as cpp/pybind/module.cpp."""
+    import inspect
+
+    import adaptivesurfacereconstruction as asr
+    sig = inspect.signature(asr.reconstruct_surface)
+    want = {"point_radius_scale": 1.0, "density_percentile_threshold": 10.0, "point_radius_estimation_knn": 24,
+            "octree_max_depth": 21, "contouring_value_threshold": 1.0,
+            "keep_n_connected_components": np.iinfo(np.int64).max, "minimum_component_size": 3}
+    for k, v in want.items():
+        assert sig.parameters[k].default == v
+    assert list(sig.parameters)[:3] == ["points", "normals", "radii"]
+    sig = inspect.signature(asr.create_octree)
+    assert [(k, p.default) for k, p in sig.parameters.items()][4:] == [("radius_scale", 1), ("grow_steps", 0),
+                                                                      ("max_depth", 21)]
+    assert inspect.signature(asr.create_grids_from_octree).parameters["voxel_info_all_levels"].default is False
+    assert inspect.signature(asr.remove_connected_components).parameters["minimum_component_size"].default == 3
+    with pytest.raises(ValueError):
+        asr.create_octree(np.zeros((4, 2), np.float32), np.zeros(4, np.float32), [0, 0, 0], [1, 1, 1])
+    with pytest.raises(ValueError):
+        asr.create_octree(np.zeros((4, 3), np.float32), np.zeros(5, np.float32), [0, 0, 0], [1, 1, 1])
+    with pytest.raises(ValueError):
+        asr.reconstruct_surface(np.zeros((4, 3)), np.zeros((3, 3)), np.zeros(4))
+    with pytest.raises(ValueError):
+        asr.remove_connected_components(np.zeros((4, 2)), np.zeros((1, 3), np.int32), 1)
+    assert isinstance(asr.get_version_str(), str) and isinstance(asr.get_third_party_notices(), str)
+
+
+def test_model_mirror_matches_reference_state_dict_layout():
+    from asr_b200 import model
+    from oracle import model_cpu
+    for levels in (3, 5, 6):
+        net = model.UNet(levels)
+        P = model_cpu.init_params(levels)
+        sd = net.state_dict()
+        assert set(sd) == set(P)
+        assert all(tuple(sd[k].shape) == tuple(P[k].shape) for k in sd)
+    net = model.seeded_weights(model.UNet(3), seed=1)
+    k, b = net.sparseconv_encblock0.first_conv()
+    assert k.shape == (55, 32, 64) and b.shape == (64,)
+    assert torch.equal(k[:, :, 56:], net.sparseconv_encblock0.conv1b.kernel)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference tree not present")
+def test_reference_model_script_imports_unmodified_on_the_product_shim():
+    code = ("import sys, warnings; warnings.filterwarnings('ignore'); sys.path[:0]=[%r, '/root/reference']; "
+            "import open3d.ml.torch as ml3d; from models.v0.net_definitions_torch import UNet5; "
+            "from asr_b200 import model; n = UNet5(with_importance='all', normalized_channels=8, "
+            "residual_skip_connection=True); m = model.UNet(5); m.load_state_dict(n.state_dict()); print('OK')"
+            % os.path.join(ROOT, "adaptive-surface-reconstruction_b200"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "OK" in r.stdout, r.stderr[-1500:]
+
+
+def test_clouds_are_deterministic_and_bench_byte_model():
+    from asr_b200 import clouds
+    a, b = clouds.thingi_like(20000, seed=2), clouds.thingi_like(20000, seed=2)
+    assert all(np.array_equal(a[k], b[k]) for k in a)
+    assert a["points"].dtype == np.float32 and a["points"].shape == (20000, 3)
+    assert np.allclose(np.linalg.norm(a["normals"], axis=1), 1, atol=1e-5) and a["radii"].min() > 0
+    sys.path.insert(0, ROOT)
+    import bench
+    sizes = {"N": 10, "V": [4, 2], "E": [20, 6], "P": 30, "D": 5, "M": 3}
+    by = bench.algorithmic_bytes(sizes, [{"V_in": 4, "V_out": 4, "E": 20, "K": 55, "Cin": 32, "Cout": 64,
+                                          "importance": True}])
+    assert by["sparse_conv_stack"] == 4 * 4 * 32 + 4 * 4 * 64 + 5 * 20 + 8 * 5 + 4 * 55 * 32 * 64 + 32
+    assert by["search"] == 12 * 10 + 16 * 4 + 12 * 30 + 8 * 5
