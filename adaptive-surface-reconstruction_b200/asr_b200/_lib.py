@@ -38,7 +38,7 @@ SIGNATURES = {
     "asr_grids_get": (_i32, [_vp, _i32] + [_vp] * 10),
     "asr_duals_count": (_i32, [_vp, _pi64, _vp]),
     "asr_duals_fill": (_i32, [_vp, _vp, _vp]),
-    "asr_radius_search_create": (_i32, [_vp, _i64, _vp, _vp, _i64, _vp, _pp, _pi64]),
+    "asr_radius_search_create": (_i32, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _pp, _pi64]),
     "asr_radius_search_fill": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "asr_radius_search_destroy": (None, [_vp]),
     "asr_scale_compatibility": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
@@ -51,6 +51,9 @@ SIGNATURES = {
     "asr_reduce_subarrays_sum": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "asr_invert_neighbors_list": (_i32, [_i64, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _vp]),
     "asr_decode": (_i32, [_vp, _vp, _i64] + [_vp] * 9),
+    "asr_packed_weights_size": (_i64, [_i32, _i32]),
+    "asr_pack_weights": (_i32, [_vp, _i32, _i32, _vp, _vp]),
+    "asr_dense_tf32x3": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp]),
     "asr_contour_count": (_i32, [_vp, _vp, _i64, _f32, _vp, _vp, _pi64, _vp]),
     "asr_contour_fill": (_i32, [_vp, _vp, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

@@ -105,6 +105,12 @@ class Octree:
         check(lib().asr_octree_get_frame(self._h, vs.ctypes.data, ivs.ctypes.data, off.ctypes.data))
         return vs, ivs, off
 
+    def search_frame(self):
+        """(origin x, y, z, finest cell size) of the octree's 2^21 grid, for multi_radius_search."""
+        vs, _, off = self.frame()
+        h = np.float32(vs[21])
+        return np.array([-np.float32(off[0]) * h, -np.float32(off[1]) * h, -np.float32(off[2]) * h, h], np.float32)
+
     def grids(self, num_levels, voxel_info_all_levels=False):
         """asr_grids_* (reference CreateGridsFromOctree, grid.cpp:245).  Returns a
         list (finest first) of dicts of CUDA tensors with the key set of
@@ -149,9 +155,11 @@ class Octree:
 # ------------------------------------------------------------------------------------ aggregation search
 
 
-def multi_radius_search(points, queries, radii):
+def multi_radius_search(points, queries, radii, frame=None):
     """(index int32[P], squared distance float32[P], row_splits int64[Q+1]);
-    d2 < r^2, ascending by d2 (reference nsearch.cpp:130-146)."""
+    d2 < r^2, ascending by d2 (reference nsearch.cpp:130-146).  `frame` =
+    (origin xyz, finest cell size) optionally aligns the internal binning grid
+    with the octree (Octree.search_frame()); it never changes the result."""
     points = _cuda(points, torch.float32, "points")
     queries = _cuda(queries, torch.float32, "queries")
     radii = _cuda(radii, torch.float32, "radii")
@@ -161,8 +169,11 @@ def multi_radius_search(points, queries, radii):
         raise ValueError("radii must have shape [num_queries]")
     h, n = C.c_void_p(0), _i64(0)
     L = lib()
+    fr = None
+    if frame is not None:
+        fr = np.ascontiguousarray(np.asarray(frame, dtype=np.float32).reshape(4))
     check(L.asr_radius_search_create(_ptr(points), points.shape[0], _ptr(queries), _ptr(radii), queries.shape[0],
-                                     _stream(), C.byref(h), C.byref(n)))
+                                     fr.ctypes.data if fr is not None else None, _stream(), C.byref(h), C.byref(n)))
     try:
         dev = points.device
         idx = torch.empty(n.value, dtype=torch.int32, device=dev)
@@ -327,6 +338,27 @@ def decode(shifts, code, w1, b1, w2, b2, w3, signed_scale=None, with_gradient=Fa
                            _ptr(_opt(signed_scale, torch.float32, "signed_scale")), _ptr(values), _ptr(grad),
                            _stream()))
     return (values, grad) if with_gradient else values
+
+
+def pack_weights(w):
+    """Packs a [in, out] fp32 matrix for dense_tf32x3 (hi/lo tf32 parts, UMMA canonical layout)."""
+    w = _cuda(w, torch.float32, "w")
+    K, N = w.shape
+    out = torch.empty(int(lib().asr_packed_weights_size(K, N)), dtype=torch.float32, device=w.device)
+    check(lib().asr_pack_weights(_ptr(w), K, N, _ptr(out), _stream()))
+    return out, K, N
+
+
+def dense_tf32x3(a, packed, bias=None, relu=False):
+    """act(a @ w + bias) on the tensor cores (tcgen05 kind::tf32, 3xTF32 split)."""
+    wp, K, N = packed
+    a = _cuda(a, torch.float32, "a")
+    if a.ndim != 2 or a.shape[1] != K:
+        raise ValueError("a must have shape [rows, %d]" % K)
+    out = torch.empty((a.shape[0], N), dtype=torch.float32, device=a.device)
+    check(lib().asr_dense_tf32x3(_ptr(a), a.shape[0], K, K, _ptr(wp), N, _ptr(_opt(bias, torch.float32, "bias")),
+                                 int(bool(relu)), _ptr(out), N, _stream()))
+    return out
 
 
 def contour_vertices(values, dual_indices, node_positions, unsigned_threshold=1.0):

@@ -55,7 +55,7 @@ def build_input_dict(points, normals, radii, bb_min, bb_max, levels=5, radius_sc
     if "voxel_centers0" not in d:  # empty tree
         d["voxel_centers0"] = torch.zeros((0, 3), dtype=torch.float32, device=points.device)
         d["voxel_sizes0"] = torch.zeros(0, dtype=torch.float32, device=points.device)
-    idx, dist, rs = ops.multi_radius_search(points, d["voxel_centers0"], d["voxel_sizes0"])
+    idx, dist, rs = ops.multi_radius_search(points, d["voxel_centers0"], d["voxel_sizes0"], frame=tree.search_frame())
     d["aggregation_neighbors_index"] = idx
     d["aggregation_neighbors_dist"] = dist
     d["aggregation_row_splits"] = rs

@@ -22,6 +22,10 @@ void contour_count(const float* values, const int64_t* duals, int64_t D, float t
                    int64_t* num_vertices, cudaStream_t s);
 void contour_fill(const float* values, const int64_t* duals, int64_t D, float thr, const float* pos,
                   const uint8_t* flag, const int64_t* offset, float* vertices, int64_t* vertex_dual, cudaStream_t s);
+size_t packed_weights_floats(int K, int N);
+void pack_weights(const float* W, int K, int N, float* out, cudaStream_t s);
+void dense_gemm_tf32x3(const float* A, int64_t M, int K, int lda, const float* Wp, int N, const float* bias, int relu,
+                       float* D, int ldd, cudaStream_t s);
 void profile_set(bool on);
 void profile_reset();
 int profile_count();
@@ -189,13 +193,15 @@ int asr_duals_fill(asr_octree* tree, int64_t* d_out, void* stream) {
 }
 
 int asr_radius_search_create(const float* d_points, int64_t num_points, const float* d_queries, const float* d_radii,
-                             int64_t num_queries, void* stream, asr_search** out, int64_t* num_pairs) {
+                             int64_t num_queries, const float* h_frame, void* stream, asr_search** out,
+                             int64_t* num_pairs) {
     return guarded([&] {
         ASRB_REQUIRE(out && num_pairs, "null argument");
         ASRB_REQUIRE(num_points >= 0 && num_queries >= 0, "negative size");
         ASRB_REQUIRE(num_points < (int64_t(1) << 31), "too many points");
         auto h = std::make_unique<asr_search>();
-        search_prepare(h->s, d_points, num_points, d_queries, d_radii, num_queries, S(stream));
+        ASRB_REQUIRE(!h_frame || h_frame[3] > 0.f, "frame cell size must be positive");
+        search_prepare(h->s, d_points, num_points, d_queries, d_radii, num_queries, h_frame, S(stream));
         *num_pairs = h->s.num_pairs;
         *out = h.release();
     });
@@ -268,6 +274,24 @@ int asr_invert_neighbors_list(int64_t num_points, const int32_t* idx, const int6
 int asr_decode(const float* shifts, const float* code, int64_t V, const float* w1, const float* b1, const float* w2,
                const float* b2, const float* w3, const float* signed_scale, float* values, float* grad, void* stream) {
     return guarded([&] { decode_mlp(shifts, code, V, w1, b1, w2, b2, w3, signed_scale, values, grad, S(stream)); });
+}
+
+int64_t asr_packed_weights_size(int in_features, int out_features) {
+    return (int64_t)packed_weights_floats(in_features, out_features);
+}
+int asr_pack_weights(const float* d_w, int in_features, int out_features, float* d_packed, void* stream) {
+    return guarded([&] {
+        ASRB_REQUIRE(in_features >= 1 && out_features >= 1 && out_features <= 256, "bad weight shape");
+        pack_weights(d_w, in_features, out_features, d_packed, S(stream));
+    });
+}
+int asr_dense_tf32x3(const float* d_a, int64_t rows, int in_features, int lda, const float* d_packed_w, int out_features,
+                     const float* d_bias, int relu, float* d_out, int ldd, void* stream) {
+    return guarded([&] {
+        ASRB_REQUIRE(rows >= 0 && in_features >= 1, "bad shape");
+        ASRB_REQUIRE(lda >= in_features && ldd >= out_features, "leading dimensions too small");
+        dense_gemm_tf32x3(d_a, rows, in_features, lda, d_packed_w, out_features, d_bias, relu, d_out, ldd, S(stream));
+    });
 }
 
 int asr_contour_count(const float* values, const int64_t* duals, int64_t D, float thr, uint8_t* flag, int64_t* offset,

@@ -7,6 +7,7 @@
 // lanes run the 37 independent probes (1 self + 6 same-level + 24 finer + 6
 // coarser) in parallel, a warp OR-reduction yields the 55-bit slot mask, and a
 // scan over popcounts gives the CSR offsets (count -> scan -> fill).
+#include "hash.cuh"
 #include "internal.h"
 #include "prims.cuh"
 #include "profile.cuh"
@@ -66,8 +67,8 @@ constexpr int kProbes = 37;
 
 // pass 1: 55-bit slot mask per voxel
 __global__ void __launch_bounds__(256)
-adjacency_mask_kernel(const Key* __restrict__ keys, long long V, unsigned long long* __restrict__ mask,
-                      int32_t* __restrict__ count) {
+adjacency_mask_kernel(const Key* __restrict__ keys, long long V, const KeyTableView table,
+                      unsigned long long* __restrict__ mask, int32_t* __restrict__ count) {
     const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= V) return;
@@ -79,7 +80,7 @@ adjacency_mask_kernel(const Key* __restrict__ keys, long long V, unsigned long l
             continue;
         }
         const Probe pr = make_probe(c, p);
-        if (pr.key && find_key(keys, V, pr.key) >= 0) m |= 1ULL << pr.slot;
+        if (pr.key && table_find(table, pr.key) >= 0) m |= 1ULL << pr.slot;
     }
     unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)m);
     unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(m >> 32));
@@ -92,8 +93,9 @@ adjacency_mask_kernel(const Key* __restrict__ keys, long long V, unsigned long l
 
 // pass 2: write (index, slot) in slot order
 __global__ void __launch_bounds__(256)
-adjacency_fill_kernel(const Key* __restrict__ keys, long long V, const unsigned long long* __restrict__ mask,
-                      const int64_t* __restrict__ splits, int32_t* __restrict__ nidx, uint8_t* __restrict__ nslot) {
+adjacency_fill_kernel(const Key* __restrict__ keys, long long V, const KeyTableView table,
+                      const unsigned long long* __restrict__ mask, const int64_t* __restrict__ splits,
+                      int32_t* __restrict__ nidx, uint8_t* __restrict__ nslot) {
     const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= V) return;
@@ -108,7 +110,7 @@ adjacency_fill_kernel(const Key* __restrict__ keys, long long V, const unsigned 
         } else {
             const Probe pr = make_probe(c, p);
             slot = pr.slot;
-            if (pr.key && ((m >> slot) & 1)) idx = find_key(keys, V, pr.key);
+            if (pr.key && ((m >> slot) & 1)) idx = table_find(table, pr.key);
         }
         if (idx >= 0) {
             const int pos = __popcll(m & ((1ULL << slot) - 1));
@@ -138,13 +140,13 @@ coarsen_keys_kernel(const Key* __restrict__ keys, long long V, Key* __restrict__
 }
 
 __global__ void __launch_bounds__(256)
-up_table_kernel(const Key* __restrict__ keys, long long V, const Key* __restrict__ coarse, long long Vc,
+up_table_kernel(const Key* __restrict__ keys, long long V, const KeyTableView coarse,
                 int32_t* __restrict__ uidx, uint8_t* __restrict__ uslot) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= V) return;
     const Key k = keys[i];
     const bool m = is_merged(keys, V, i);
-    uidx[i] = (int32_t)lower_bound_key(coarse, Vc, m ? (k >> 3) : k);
+    uidx[i] = (int32_t)table_find(coarse, m ? (k >> 3) : k);  // always present (grid.cpp:211-215)
     uslot[i] = m ? (uint8_t)(k & 7) : (uint8_t)8;
 }
 
@@ -175,14 +177,15 @@ __global__ void first_nokey_kernel(const Key* __restrict__ a, long long n, int64
     *out = lower_bound_key(a, n, kNoKey);
 }
 
-static void build_adjacency(GridLevel& g, cudaStream_t s) {
+static void build_adjacency(GridLevel& g, const KeyTable& table, cudaStream_t s) {
     const long long V = g.V;
     g.nsplits.alloc((size_t)V + 1, s);
     DevBuf<unsigned long long> mask((size_t)V, s);
     DevBuf<int32_t> count((size_t)V, s);
     if (V) {
         ProfileScope prof("adjacency_mask", s);
-        adjacency_mask_kernel<<<grid_for((size_t)V * 32, 256), 256, 0, s>>>(g.keys.get(), V, mask.get(), count.get());
+        adjacency_mask_kernel<<<grid_for((size_t)V * 32, 256), 256, 0, s>>>(g.keys.get(), V, table.view(), mask.get(),
+                                                                            count.get());
         ASRB_CHECK_LAUNCH();
     }
     exclusive_sum_i32_to_i64(count.get(), g.nsplits.get(), (size_t)V, s);
@@ -191,7 +194,7 @@ static void build_adjacency(GridLevel& g, cudaStream_t s) {
     g.nslot.alloc((size_t)g.E, s);
     if (V) {
         ProfileScope prof("adjacency_fill", s);
-        adjacency_fill_kernel<<<grid_for((size_t)V * 32, 256), 256, 0, s>>>(g.keys.get(), V, mask.get(),
+        adjacency_fill_kernel<<<grid_for((size_t)V * 32, 256), 256, 0, s>>>(g.keys.get(), V, table.view(), mask.get(),
                                                                             g.nsplits.get(), g.nidx.get(),
                                                                             g.nslot.get());
         ASRB_CHECK_LAUNCH();
@@ -206,6 +209,7 @@ void grids_build(Octree& t, int num_levels, bool all_info, cudaStream_t s) {
     for (int l = 0; l <= kMaxLevel; ++l) vf.vs[l] = t.frame.vs[l];
     for (int a = 0; a < 3; ++a) vf.off[a] = t.frame.off[a];
 
+    KeyTable table;  // keys of the level being built -> position
     for (int l = 0; l < num_levels; ++l) {
         auto g = std::make_unique<GridLevel>();
         if (l == 0) {
@@ -214,6 +218,7 @@ void grids_build(Octree& t, int num_levels, bool all_info, cudaStream_t s) {
             if (g->V)
                 ASRB_CUDA(cudaMemcpyAsync(g->keys.get(), t.leaves.get(), (size_t)g->V * sizeof(Key),
                                           cudaMemcpyDeviceToDevice, s));
+            table.build(g->keys.get(), (size_t)g->V, s);
         } else {
             GridLevel& prev = *t.grids.back();
             const long long V = prev.V;
@@ -237,9 +242,10 @@ void grids_build(Octree& t, int num_levels, bool all_info, cudaStream_t s) {
             prev.uidx.alloc((size_t)V, s);
             prev.uslot.alloc((size_t)V, s);
             prev.has_up = true;
+            table.build(g->keys.get(), Vc, s);
             if (V) {
-                up_table_kernel<<<grid_for(V, 256), 256, 0, s>>>(prev.keys.get(), V, g->keys.get(), (long long)Vc,
-                                                                 prev.uidx.get(), prev.uslot.get());
+                up_table_kernel<<<grid_for(V, 256), 256, 0, s>>>(prev.keys.get(), V, table.view(), prev.uidx.get(),
+                                                                 prev.uslot.get());
                 ASRB_CHECK_LAUNCH();
             }
         }
@@ -252,17 +258,16 @@ void grids_build(Octree& t, int num_levels, bool all_info, cudaStream_t s) {
                 ASRB_CHECK_LAUNCH();
             }
         }
-        build_adjacency(*g, s);
+        build_adjacency(*g, table, s);
         t.grids.push_back(std::move(g));
     }
 }
 
 // ------------------------------------------------------------------ dual cells
 // node lookup against the sorted sibling groups: returns node index or -1
-__device__ __forceinline__ long long node_index(const Key* __restrict__ groups, long long ng, int root_separate,
-                                                bool any, Key k) {
-    if (k == 1 && root_separate) return any ? 0 : -1;
-    const long long gi = find_key(groups, ng, k & ~Key(7));
+__device__ __forceinline__ long long node_index(const KeyTableView groups, int root_separate, Key k) {
+    if (k == 1 && root_separate) return 0;
+    const long long gi = table_find(groups, k & ~Key(7));
     if (gi < 0) return -1;
     return gi * 8 + (long long)(k & 7) + (root_separate ? 1 : 0);
 }
@@ -280,8 +285,7 @@ __device__ __forceinline__ bool dual_corner(const Cell& c, int i, int& vx, int& 
 // dual cell unless one of the 7 other same-level cells around it is an interior
 // node (a finer leaf owns the vertex) or a leaf with a smaller key (grid.cpp:334-360).
 __global__ void __launch_bounds__(256)
-dual_flag_kernel(const Key* __restrict__ leaves, long long V, const Key* __restrict__ groups, long long ng,
-                 int root_separate, const uint8_t* __restrict__ node_leaf, uint8_t* __restrict__ mask,
+dual_flag_kernel(const Key* __restrict__ leaves, long long V, const KeyTableView groups, int root_separate, const uint8_t* __restrict__ node_leaf, uint8_t* __restrict__ mask,
                  uint8_t* __restrict__ count) {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long leaf_i = t >> 3;
@@ -296,7 +300,7 @@ dual_flag_kernel(const Key* __restrict__ leaves, long long V, const Key* __restr
             for (int j = 0; j < 8 && emit; ++j) {
                 if (j == i) continue;
                 const Key a = cell_key(vx - (j & 1), vy - ((j >> 1) & 1), vz - ((j >> 2) & 1), c.lev);
-                const long long ni = node_index(groups, ng, root_separate, true, a);
+                const long long ni = node_index(groups, root_separate, a);
                 if (ni < 0) continue;
                 if (!node_leaf[ni] || a < leaf) emit = false;
             }
@@ -311,8 +315,7 @@ dual_flag_kernel(const Key* __restrict__ leaves, long long V, const Key* __restr
 }
 
 __global__ void __launch_bounds__(256)
-dual_fill_kernel(const Key* __restrict__ leaves, long long V, const Key* __restrict__ groups, long long ng,
-                 int root_separate, const uint8_t* __restrict__ node_leaf, const int64_t* __restrict__ node_rank,
+dual_fill_kernel(const Key* __restrict__ leaves, long long V, const KeyTableView groups, int root_separate, const uint8_t* __restrict__ node_leaf, const int64_t* __restrict__ node_rank,
                  const uint8_t* __restrict__ mask, const int64_t* __restrict__ offset, int64_t* __restrict__ out,
                  int* __restrict__ error) {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -328,7 +331,7 @@ dual_fill_kernel(const Key* __restrict__ leaves, long long V, const Key* __restr
     for (int j = 0; j < 8; ++j) {
         Key a = cell_key(vx - (j & 1), vy - ((j >> 1) & 1), vz - ((j >> 2) & 1), c.lev);
         long long ni = -1;
-        while (a && (ni = node_index(groups, ng, root_separate, true, a)) < 0) a >>= 3;  // walk up (grid.cpp:429-433)
+        while (a && (ni = node_index(groups, root_separate, a)) < 0) a >>= 3;  // walk up (grid.cpp:429-433)
         if (ni < 0 || !node_leaf[ni]) {
             *error = 1;  // the reference throws here (grid.cpp:434-440)
             row[j] = 0;
@@ -346,7 +349,7 @@ void duals_count(Octree& t, cudaStream_t s) {
     DevBuf<uint8_t> count((size_t)V, s);
     if (V) {
         ProfileScope prof("dual_flag", s);
-        dual_flag_kernel<<<grid_for((size_t)V * 8, 256), 256, 0, s>>>(t.leaves.get(), V, t.groups.get(), t.num_groups,
+        dual_flag_kernel<<<grid_for((size_t)V * 8, 256), 256, 0, s>>>(t.leaves.get(), V, t.group_table.view(),
                                                                       t.root_separate, t.node_leaf.get(),
                                                                       t.dual_mask.get(), count.get());
         ASRB_CHECK_LAUNCH();
@@ -362,7 +365,7 @@ void duals_fill(Octree& t, int64_t* d_out, cudaStream_t s) {
     DevBuf<int> err(1, s);
     ASRB_CUDA(cudaMemsetAsync(err.get(), 0, sizeof(int), s));
     ProfileScope prof("dual_fill", s);
-    dual_fill_kernel<<<grid_for((size_t)V * 8, 256), 256, 0, s>>>(t.leaves.get(), V, t.groups.get(), t.num_groups,
+    dual_fill_kernel<<<grid_for((size_t)V * 8, 256), 256, 0, s>>>(t.leaves.get(), V, t.group_table.view(),
                                                                   t.root_separate, t.node_leaf.get(),
                                                                   t.node_rank.get(), t.dual_mask.get(),
                                                                   t.dual_offset.get(), d_out, err.get());

@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "hash.cuh"
 
 namespace asrb {
 
@@ -38,6 +39,7 @@ struct Octree {
     int64_t num_nodes = 0;
     int64_t num_leaves = 0;
     DevBuf<Key> groups;
+    KeyTable group_table;          // group key -> position in `groups`
     DevBuf<uint8_t> node_leaf;     // [num_nodes] 1 = leaf
     DevBuf<int64_t> node_rank;     // [num_nodes+1] exclusive scan of node_leaf
     DevBuf<Key> leaves;            // [num_leaves] ascending

@@ -114,9 +114,7 @@ ancestor_kernel(const Key* __restrict__ groups, long long n, Key* __restrict__ o
     }
 }
 
-__device__ __forceinline__ bool has_group(const Key* __restrict__ groups, long long n, Key g) {
-    return find_key(groups, n, g) >= 0;
-}
+__device__ __forceinline__ bool has_group(const KeyTableView groups, Key g) { return table_find(groups, g) >= 0; }
 
 // One round of face balancing (octree.cpp:152-206), evaluated against a snapshot
 // of the node set.  Thread = (frontier group, face).  A group whose first
@@ -124,8 +122,8 @@ __device__ __forceinline__ bool has_group(const Key* __restrict__ groups, long l
 // missing neighbour the chain of sibling groups up to the first existing
 // ancestor is appended to `out`.
 __global__ void __launch_bounds__(256)
-balance_round_kernel(const Key* __restrict__ frontier, long long nf, const Key* __restrict__ groups,
-                     long long ng, Key* __restrict__ out, unsigned long long cap,
+balance_round_kernel(const Key* __restrict__ frontier, long long nf, const KeyTableView groups,
+                     Key* __restrict__ out, unsigned long long cap,
                      unsigned long long* __restrict__ out_count) {
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= nf * 6) return;
@@ -133,7 +131,7 @@ balance_round_kernel(const Key* __restrict__ frontier, long long nf, const Key* 
     const int face = (int)(t % 6);
     if (g == 0) return;  // key 0 counts as having a first child (itself)
     // leaf test on the first sibling (octreebase.h:174-182)
-    if (__clzll((long long)g) > 1 && has_group(groups, ng, g << 3)) return;
+    if (__clzll((long long)g) > 1 && has_group(groups, g << 3)) return;
     const Cell pc = key_cell(g >> 3);
     int d[3] = {0, 0, 0};
     d[face % 3] = face < 3 ? -1 : 1;
@@ -141,7 +139,7 @@ balance_round_kernel(const Key* __restrict__ frontier, long long nf, const Key* 
     if (!k) return;
     while (k > 1) {
         const Key kg = k & ~Key(7);
-        if (has_group(groups, ng, kg)) break;
+        if (has_group(groups, kg)) break;
         const unsigned long long pos = atomicAdd(out_count, 1ULL);
         if (pos < cap) out[pos] = kg;
         k >>= 3;
@@ -149,7 +147,7 @@ balance_round_kernel(const Key* __restrict__ frontier, long long nf, const Key* 
 }
 
 __global__ void __launch_bounds__(256)
-leaf_flag_kernel(const Key* __restrict__ groups, long long ng, int root_separate, long long num_nodes,
+leaf_flag_kernel(const Key* __restrict__ groups, const KeyTableView table, int root_separate, long long num_nodes,
                  uint8_t* __restrict__ flag) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= num_nodes) return;
@@ -158,7 +156,7 @@ leaf_flag_kernel(const Key* __restrict__ groups, long long ng, int root_separate
     else k = groups[i >> 3] + Key(i & 7);
     bool child = false;
     if (k == 0) child = true;  // contains(0 << 3)
-    else if (__clzll((long long)k) > 1) child = has_group(groups, ng, k << 3);
+    else if (__clzll((long long)k) > 1) child = has_group(table, k << 3);
     flag[i] = child ? 0 : 1;
 }
 
@@ -229,16 +227,17 @@ void octree_build(Octree& t, const float* d_points, const float* d_radii, int64_
     if (ng) ASRB_CUDA(cudaMemcpyAsync(frontier.get(), groups.get(), ng * sizeof(Key), cudaMemcpyDeviceToDevice, s));
     DevBuf<unsigned long long> counter(1, s);
     t.balance_rounds = 0;
+    KeyTable table;
     while (nf > 0) {
+        table.build(groups.get(), ng, s);
         size_t cap = std::max<size_t>(nf * 4, 1 << 16);
         DevBuf<Key> emitted;
         unsigned long long produced = 0;
         for (;;) {
             emitted.alloc(cap, s);
             ASRB_CUDA(cudaMemsetAsync(counter.get(), 0, sizeof(unsigned long long), s));
-            balance_round_kernel<<<grid_for(nf * 6, 256), 256, 0, s>>>(frontier.get(), (long long)nf, groups.get(),
-                                                                      (long long)ng, emitted.get(), cap,
-                                                                      counter.get());
+            balance_round_kernel<<<grid_for(nf * 6, 256), 256, 0, s>>>(frontier.get(), (long long)nf, table.view(),
+                                                                      emitted.get(), cap, counter.get());
             ASRB_CHECK_LAUNCH();
             produced = d2h_scalar(counter.get(), s);
             if (produced <= cap) break;
@@ -267,11 +266,12 @@ void octree_build(Octree& t, const float* d_points, const float* d_radii, int64_
     t.root_separate = t.any && !group0;
     t.num_nodes = (int64_t)ng * 8 + (t.root_separate ? 1 : 0);
     t.groups = std::move(groups);
+    t.group_table.build(t.groups.get(), ng, s);
     t.node_leaf.alloc((size_t)t.num_nodes, s);
     t.node_rank.alloc((size_t)t.num_nodes + 1, s);
     if (t.num_nodes) {
-        leaf_flag_kernel<<<grid_for(t.num_nodes, 256), 256, 0, s>>>(t.groups.get(), (long long)ng, t.root_separate,
-                                                                    t.num_nodes, t.node_leaf.get());
+        leaf_flag_kernel<<<grid_for(t.num_nodes, 256), 256, 0, s>>>(t.groups.get(), t.group_table.view(),
+                                                                    t.root_separate, t.num_nodes, t.node_leaf.get());
         ASRB_CHECK_LAUNCH();
     }
     exclusive_sum_u8_to_i64(t.node_leaf.get(), t.node_rank.get(), (size_t)t.num_nodes, s);

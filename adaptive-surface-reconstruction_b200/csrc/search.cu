@@ -17,6 +17,7 @@
 // Squared distances are evaluated as ((dx*dx) + dy*dy) + dz*dz in fp32 without
 // FMA contraction, the order nanoflann's L2 adaptor uses for dim 3, so that the
 // strict `<` test resolves boundary points identically.
+#include "hash.cuh"
 #include "internal.h"
 #include "prims.cuh"
 #include "profile.cuh"
@@ -102,67 +103,154 @@ gather_points_kernel(const float* __restrict__ pts, const uint32_t* __restrict__
 
 constexpr int kWarpsPerBlock = 8;
 
+// ------------------------------------------------------------------ cell index
+// For every power-of-two cell size that some query needs, the non-empty cells of
+// the Morton-sorted point array are entered in a hash table
+//     (cell code | level marker)  ->  [begin, end) window of the sorted points,
+// so a query resolves each covering cell with ~1.5 probes.  Position j of the
+// sorted array starts a new cell at shift sh iff the highest bit in which its
+// code differs from its predecessor's lies at or above 3*sh, so one pass over
+// the points serves all levels.
+__device__ __forceinline__ Key cell_key_at(Key code, int sh) {
+    return (code >> (3 * sh)) | (Key(1) << (3 * (kGridBits - sh)));
+}
+__device__ __forceinline__ int boundary_top_shift(const Key* __restrict__ codes, long long j) {
+    if (j == 0) return kGridBits;
+    const Key d = codes[j] ^ codes[j - 1];
+    return d ? (63 - __clzll((long long)d)) / 3 : -1;
+}
+
+// ball -> conservative integer box [lo, hi] on the 2^21 grid and the smallest
+// shift at which it spans <= 3 cells per axis
+__device__ __forceinline__ int query_box(const float* __restrict__ q, float r, const BinFrame& f, int lo[3], int hi[3]) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float pad = __fmaf_rn(r, 1.00001f, fabsf(q[a]) * 4e-7f);  // a few ulps of the coordinates
+        lo[a] = bin_coord(q[a] - pad, f.origin[a], f.inv_h);
+        hi[a] = bin_coord(q[a] + pad, f.origin[a], f.inv_h);
+    }
+    const int span = max(max(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]) + 1;
+    int sh = span <= 3 ? 0 : max(0, 30 - __clz(span));  // 2^(sh+2) > span: a first guess, then refine
+    while (sh < kGridBits && (((hi[0] >> sh) - (lo[0] >> sh)) > 2 || ((hi[1] >> sh) - (lo[1] >> sh)) > 2 ||
+                              ((hi[2] >> sh) - (lo[2] >> sh)) > 2))
+        ++sh;
+    return sh;
+}
+
+__global__ void __launch_bounds__(256)
+query_levels_kernel(const float* __restrict__ queries, const float* __restrict__ radii, long long nq, BinFrame f,
+                    unsigned* __restrict__ level_mask) {
+    long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    unsigned m = 0;
+    if (q < nq) {
+        const float r = radii[q];
+        if (r >= 0.0f) {
+            int lo[3], hi[3];
+            m = 1u << query_box(queries + 3 * q, r, f, lo, hi);
+        }
+    }
+    m = __reduce_or_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicOr(level_mask, m);
+}
+
+__global__ void __launch_bounds__(256)
+cell_count_kernel(const Key* __restrict__ codes, long long n, unsigned levels, unsigned long long* __restrict__ total) {
+    long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    unsigned c = 0;
+    if (j < n) {
+        const int top = boundary_top_shift(codes, j);
+        if (top >= 0) c = __popc(levels & ((2u << top) - 1u));
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, (unsigned long long)c);
+}
+
+__global__ void __launch_bounds__(256)
+cell_insert_kernel(const Key* __restrict__ codes, long long n, unsigned levels, HashEntry* __restrict__ e, uint32_t mask) {
+    long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int top = boundary_top_shift(codes, j);
+    if (top < 0) return;
+    unsigned lv = levels & ((2u << top) - 1u);
+    const Key code = codes[j];
+    while (lv) {
+        const int sh = __ffs(lv) - 1;
+        lv &= lv - 1;
+        const Key k = cell_key_at(code, sh);
+        uint32_t s = hash_key(k) & mask;
+        for (;;) {
+            const Key prev = atomicCAS(&e[s].key, kNoKey, k);
+            if (prev == kNoKey) {
+                e[s].val = j;  // begin; the end is filled in by cell_end_kernel
+                break;
+            }
+            s = (s + 1) & mask;
+        }
+    }
+}
+
+// the cell that ends at position j (exclusive) is the one containing point j-1
+__global__ void __launch_bounds__(256)
+cell_end_kernel(const Key* __restrict__ codes, long long n, unsigned levels, HashEntry* __restrict__ e, uint32_t mask) {
+    long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x + 1;
+    if (j > n) return;
+    const int top = j == n ? kGridBits : boundary_top_shift(codes, j);
+    if (top < 0) return;
+    unsigned lv = levels & ((2u << top) - 1u);
+    const Key code = codes[j - 1];
+    while (lv) {
+        const int sh = __ffs(lv) - 1;
+        lv &= lv - 1;
+        const Key k = cell_key_at(code, sh);
+        uint32_t s = hash_key(k) & mask;
+        while (e[s].key != k) s = (s + 1) & mask;
+        e[s].val |= (long long)j << 32;
+    }
+}
+
 template <bool FILL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-ball_query_kernel(const Key* __restrict__ codes, const float4* __restrict__ spts, long long n, BinFrame f,
+ball_query_kernel(const KeyTableView cells, const float4* __restrict__ spts, BinFrame f,
                   const float* __restrict__ queries, const float* __restrict__ radii, long long nq,
                   int32_t* __restrict__ counts, const int64_t* __restrict__ splits,
                   unsigned long long* __restrict__ out_keys) {
-    __shared__ long long s_begin[kWarpsPerBlock][8];
-    __shared__ int s_pre[kWarpsPerBlock][9];
+    __shared__ unsigned s_begin[kWarpsPerBlock][32];
+    __shared__ int s_pre[kWarpsPerBlock][33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long q = blockIdx.x * (long long)kWarpsPerBlock + warp;
     if (q >= nq) return;
     const float qx = queries[3 * q], qy = queries[3 * q + 1], qz = queries[3 * q + 2];
     const float r = radii[q];
     const float r2 = __fmul_rn(r, r);
-    // conservative integer box of the ball: pad by a few ulps of the coordinates
-    int lo[3], hi[3];
-    {
-        const float c[3] = {qx, qy, qz};
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const float pad = __fmaf_rn(r, 1.00001f, fabsf(c[a]) * 4e-7f);
-            lo[a] = bin_coord(c[a] - pad, f.origin[a], f.inv_h);
-            hi[a] = bin_coord(c[a] + pad, f.origin[a], f.inv_h);
-        }
-    }
-    // smallest power-of-two cell size that covers the box with <= 2 cells per axis
-    const int span = max(max(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]) + 1;
-    const int sh = span <= 1 ? 0 : 32 - __clz(span - 1);  // 2^sh >= span
-    long long pos = 0;
-    if (lane < 16) {
-        const int cell = lane >> 1;
-        const int cx = (lo[0] >> sh) + (cell & 1), cy = (lo[1] >> sh) + ((cell >> 1) & 1),
-                  cz = (lo[2] >> sh) + ((cell >> 2) & 1);
-        const bool valid = r >= 0.0f && cx <= (hi[0] >> sh) && cy <= (hi[1] >> sh) && cz <= (hi[2] >> sh);
-        if (valid) {
-            if (sh >= kGridBits) {
-                pos = (lane & 1) ? n : 0;
-            } else {
-                const Key base = morton3(cx, cy, cz) << (3 * sh);
-                const Key bound = (lane & 1) ? base + (Key(1) << (3 * sh)) : base;
-                pos = lower_bound_key(codes, n, bound);
+    int len = 0;
+    unsigned begin = 0;
+    if (r >= 0.0f) {
+        int lo[3], hi[3];
+        const float qq[3] = {qx, qy, qz};
+        const int sh = query_box(qq, r, f, lo, hi);
+        if (lane < 27) {
+            const int cx = (lo[0] >> sh) + lane % 3, cy = (lo[1] >> sh) + (lane / 3) % 3, cz = (lo[2] >> sh) + lane / 9;
+            if (cx <= (hi[0] >> sh) && cy <= (hi[1] >> sh) && cz <= (hi[2] >> sh)) {
+                const Key k = morton3(cx, cy, cz) | (Key(1) << (3 * (kGridBits - sh)));
+                const long long v = table_find(cells, k);
+                if (v >= 0) {
+                    begin = (unsigned)v;
+                    len = (int)((unsigned long long)v >> 32) - (int)begin;
+                }
             }
         }
     }
-    const long long b = __shfl_sync(0xffffffffu, pos, (lane & 7) * 2);
-    const long long e = __shfl_sync(0xffffffffu, pos, (lane & 7) * 2 + 1);
-    int len = (int)(e - b);
-    // inclusive prefix over the 8 cells (lanes 0..7 hold distinct cells)
-    int pre = len;
+    int pre = len;  // inclusive prefix over the lanes
 #pragma unroll
-    for (int d = 1; d < 8; d <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, pre, d, 8);
-        if ((lane & 7) >= d) pre += v;
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, pre, d);
+        if (lane >= d) pre += v;
     }
-    if (lane < 8) {
-        s_begin[warp][lane] = b;
-        s_pre[warp][lane + 1] = pre;
-        if (lane == 0) s_pre[warp][0] = 0;
-    }
+    s_begin[warp][lane] = begin;
+    s_pre[warp][lane + 1] = pre;
+    if (lane == 0) s_pre[warp][0] = 0;
     __syncwarp();
-    const int total = s_pre[warp][8];
+    const int total = __shfl_sync(0xffffffffu, pre, 31);
     int found = 0;
     const int64_t out_base = FILL ? splits[q] : 0;
     for (int t0 = 0; t0 < total; t0 += 32) {
@@ -170,10 +258,11 @@ ball_query_kernel(const Key* __restrict__ codes, const float4* __restrict__ spts
         bool hit = false;
         unsigned long long key = 0;
         if (t < total) {
-            int c = 0;
+            int c = 0;  // last cell with s_pre[c] <= t
 #pragma unroll
-            for (int k = 1; k < 8; ++k) c += (t >= s_pre[warp][k]) ? 1 : 0;
-            const float4 p = __ldg(spts + s_begin[warp][c] + (t - s_pre[warp][c]));
+            for (int step = 16; step > 0; step >>= 1)
+                if (c + step < 32 && s_pre[warp][c + step] <= t) c += step;
+            const float4 p = __ldg(spts + s_begin[warp][c] + (unsigned)(t - s_pre[warp][c]));
             const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
             const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
             hit = d2 < r2;
@@ -231,32 +320,39 @@ scale_compat_kernel(const float* __restrict__ sizes, const float* __restrict__ r
 }
 
 void search_prepare(Search& S, const float* d_points, int64_t n, const float* d_queries, const float* d_radii,
-                    int64_t nq, cudaStream_t s) {
+                    int64_t nq, const float* h_frame, cudaStream_t s) {
     S.n = n;
     S.nq = nq;
     S.queries = d_queries;
     S.radii = d_radii;
-    // bounding cube of the points
-    DevBuf<unsigned> mm(6, s);
-    ASRB_CUDA(cudaMemsetAsync(mm.get(), 0xff, 3 * sizeof(unsigned), s));
-    ASRB_CUDA(cudaMemsetAsync(mm.get() + 3, 0, 3 * sizeof(unsigned), s));
-    unsigned h[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0, 0, 0};
-    if (n > 0) {
-        const unsigned blocks = (unsigned)std::min<size_t>(grid_for(n, 256), 148 * 8);
-        bbox_kernel<<<blocks, 256, 0, s>>>(d_points, n, mm.get(), mm.get() + 3);
-        ASRB_CHECK_LAUNCH();
-        ASRB_CUDA(cudaMemcpyAsync(h, mm.get(), sizeof(h), cudaMemcpyDeviceToHost, s));
-        ASRB_CUDA(cudaStreamSynchronize(s));
+    if (h_frame) {
+        // caller-supplied binning frame (origin, finest cell size): the pipeline passes
+        // the octree's, which makes the cells coincide with the voxels being queried
+        for (int a = 0; a < 3; ++a) S.frame_origin[a] = h_frame[a];
+        S.frame_inv_h = 1.0f / h_frame[3];
+    } else {
+        // bounding cube of the points
+        DevBuf<unsigned> mm(6, s);
+        ASRB_CUDA(cudaMemsetAsync(mm.get(), 0xff, 3 * sizeof(unsigned), s));
+        ASRB_CUDA(cudaMemsetAsync(mm.get() + 3, 0, 3 * sizeof(unsigned), s));
+        unsigned h[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0, 0, 0};
+        if (n > 0) {
+            const unsigned blocks = (unsigned)std::min<size_t>(grid_for(n, 256), 148 * 8);
+            bbox_kernel<<<blocks, 256, 0, s>>>(d_points, n, mm.get(), mm.get() + 3);
+            ASRB_CHECK_LAUNCH();
+            ASRB_CUDA(cudaMemcpyAsync(h, mm.get(), sizeof(h), cudaMemcpyDeviceToHost, s));
+            ASRB_CUDA(cudaStreamSynchronize(s));
+        }
+        float edge = 0.f;
+        for (int a = 0; a < 3; ++a) {
+            const float lo = h[a] == 0xffffffffu ? 0.f : from_ordered_bits(h[a]);
+            const float hi = h[3 + a] == 0 ? 0.f : from_ordered_bits(h[3 + a]);
+            S.frame_origin[a] = lo;
+            edge = std::max(edge, hi - lo);
+        }
+        if (!(edge > 0.f)) edge = 1.f;
+        S.frame_inv_h = (float)(2097152.0 / ((double)edge * 1.000001));
     }
-    float edge = 0.f;
-    for (int a = 0; a < 3; ++a) {
-        const float lo = h[a] == 0xffffffffu ? 0.f : from_ordered_bits(h[a]);
-        const float hi = h[3 + a] == 0 ? 0.f : from_ordered_bits(h[3 + a]);
-        S.frame_origin[a] = lo;
-        edge = std::max(edge, hi - lo);
-    }
-    if (!(edge > 0.f)) edge = 1.f;
-    S.frame_inv_h = (float)(2097152.0 / ((double)edge * 1.000001));
     BinFrame f{{S.frame_origin[0], S.frame_origin[1], S.frame_origin[2]}, S.frame_inv_h};
 
     S.codes.alloc((size_t)n, s);
@@ -270,14 +366,44 @@ void search_prepare(Search& S, const float* d_points, int64_t n, const float* d_
         gather_points_kernel<<<grid_for(n, 256), 256, 0, s>>>(d_points, order.get(), n, (float4*)S.spts.get());
         ASRB_CHECK_LAUNCH();
     }
+    // cell index for the cell sizes the queries need
+    {
+        ProfileScope prof("search_cell_index", s);
+        DevBuf<unsigned long long> scal(2, s);
+        ASRB_CUDA(cudaMemsetAsync(scal.get(), 0, 2 * sizeof(unsigned long long), s));
+        unsigned* d_levels = reinterpret_cast<unsigned*>(scal.get() + 1);
+        if (nq > 0) {
+            query_levels_kernel<<<grid_for(nq, 256), 256, 0, s>>>(d_queries, d_radii, nq, f, d_levels);
+            ASRB_CHECK_LAUNCH();
+        }
+        unsigned levels = d2h_scalar(d_levels, s);
+        levels &= (2u << kGridBits) - 1u;
+        if (n > 0 && levels) {
+            cell_count_kernel<<<grid_for(n, 256), 256, 0, s>>>(S.codes.get(), n, levels, scal.get());
+            ASRB_CHECK_LAUNCH();
+        }
+        const unsigned long long ncells = d2h_scalar(scal.get(), s);
+        size_t cap = 64;
+        while (cap < 2 * ncells) cap <<= 1;
+        S.cells.mask = (uint32_t)(cap - 1);
+        S.cells.entries.alloc(cap, s);
+        ASRB_CUDA(cudaMemsetAsync(S.cells.entries.get(), 0xff, cap * sizeof(HashEntry), s));  // key = kNoKey, val = -1
+        if (n > 0 && levels) {
+            cell_insert_kernel<<<grid_for(n, 256), 256, 0, s>>>(S.codes.get(), n, levels, S.cells.entries.get(),
+                                                                S.cells.mask);
+            ASRB_CHECK_LAUNCH();
+            cell_end_kernel<<<grid_for(n, 256), 256, 0, s>>>(S.codes.get(), n, levels, S.cells.entries.get(),
+                                                             S.cells.mask);
+            ASRB_CHECK_LAUNCH();
+        }
+    }
     // count pass
     DevBuf<int32_t> counts((size_t)nq, s);
     S.splits.alloc((size_t)nq + 1, s);
     if (nq > 0) {
         ProfileScope prof("ball_query_count", s);
         ball_query_kernel<false><<<grid_for(nq, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
-                S.codes.get(), (const float4*)S.spts.get(), n, f, d_queries, d_radii, nq, counts.get(), nullptr,
-                nullptr);
+                S.cells.view(), (const float4*)S.spts.get(), f, d_queries, d_radii, nq, counts.get(), nullptr, nullptr);
         ASRB_CHECK_LAUNCH();
     }
     exclusive_sum_i32_to_i64(counts.get(), S.splits.get(), (size_t)nq, s);
@@ -292,8 +418,7 @@ void search_fill(Search& S, int32_t* d_idx, float* d_d2, int64_t* d_splits, cuda
     DevBuf<unsigned long long> keys((size_t)S.num_pairs, s);
     ProfileScope prof("ball_query_fill_sort", s);
     ball_query_kernel<true><<<grid_for(S.nq, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
-            S.codes.get(), (const float4*)S.spts.get(), S.n, f, S.queries, S.radii, S.nq, nullptr, S.splits.get(),
-            keys.get());
+            S.cells.view(), (const float4*)S.spts.get(), f, S.queries, S.radii, S.nq, nullptr, S.splits.get(), keys.get());
     ASRB_CHECK_LAUNCH();
     row_sort_kernel<<<grid_for((size_t)S.nq * 32, 256), 256, 0, s>>>(keys.get(), S.splits.get(), S.nq, d_idx, d_d2);
     ASRB_CHECK_LAUNCH();

@@ -1,5 +1,6 @@
 #pragma once
 #include "common.cuh"
+#include "hash.cuh"
 
 namespace asrb {
 
@@ -15,11 +16,12 @@ struct Search {
     float frame_inv_h = 1.f;
     DevBuf<Key> codes;       // sorted Morton codes of the points
     DevBuf<Float4Pod> spts;  // points in sorted order, w = original index bits
+    KeyTable cells;          // (cell code | level marker) -> begin | end << 32 in the sorted points
     DevBuf<int64_t> splits;  // [nq+1]
 };
 
 void search_prepare(Search& S, const float* d_points, int64_t n, const float* d_queries, const float* d_radii,
-                    int64_t nq, cudaStream_t s);
+                    int64_t nq, const float* h_frame, cudaStream_t s);
 void search_fill(Search& S, int32_t* d_idx, float* d_d2, int64_t* d_splits, cudaStream_t s);
 void scale_compat(const float* d_sizes, const float* d_radii, const int32_t* d_idx, const int64_t* d_splits,
                   int64_t nq, float* d_out, cudaStream_t s);

@@ -43,16 +43,24 @@ constexpr int LDA = KC + 4;    // padded row stride of the A tile (floats)
 constexpr int kThreads = 256;  // 16 x 16
 
 // ------------------------------------------------------------------ plan
+// Pairs are ordered by (row block, kernel slot): rows are cut into blocks of
+// 2^kRowBlockShift consecutive output voxels (spatially compact, the grids are
+// Morton-ordered within a level) and, inside a block, sorted stably by slot.  A
+// block's gathers and reductions then stay L2-resident while its <=55 slot runs
+// are processed, and W[slot] is still reused by whole 128-pair tiles.
+constexpr int kRowBlockShift = 15;
+
 __global__ void __launch_bounds__(256)
 entry_rows_kernel(const int64_t* __restrict__ splits, long long V, const uint8_t* __restrict__ slot,
-                  uint32_t* __restrict__ rows, uint8_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                  uint32_t* __restrict__ rows, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const long long v = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3;
     const int sub = threadIdx.x & 7;
     if (v >= V) return;
     const int64_t e = splits[v + 1];
+    const uint32_t hi = (uint32_t)(v >> kRowBlockShift) << 8;
     for (int64_t j = splits[v] + sub; j < e; j += 8) {
         rows[j] = (uint32_t)v;
-        keys[j] = slot[j];
+        keys[j] = hi | slot[j];
         vals[j] = (uint32_t)j;
     }
 }
@@ -68,41 +76,43 @@ gather_pairs_kernel(const uint32_t* __restrict__ perm, const uint32_t* __restric
     p_out[j] = (int32_t)rows[e];
 }
 
-__device__ __forceinline__ long long lower_bound_u8(const uint8_t* a, long long n, int k) {
+__device__ __forceinline__ long long lower_bound_u32(const uint32_t* a, long long n, uint32_t k) {
     long long lo = 0, hi = n;
     while (lo < hi) {
         long long mid = (lo + hi) >> 1;
-        if ((int)a[mid] < k) lo = mid + 1;
+        if (a[mid] < k) lo = mid + 1;
         else hi = mid;
     }
     return lo;
 }
 
-// one block: slot run boundaries, then the tile list (slot, first pair, count)
+// one block: (row block, slot) run boundaries, then the tile list (slot, first pair, count)
 __global__ void __launch_bounds__(256)
-tile_list_kernel(const uint8_t* __restrict__ sorted_slot, long long E, int K, int4* __restrict__ tiles,
-                 int* __restrict__ num_tiles, int* __restrict__ slot_begin) {
-    __shared__ long long s_begin[257];
-    __shared__ int s_tile0[257];
-    for (int k = threadIdx.x; k <= K; k += blockDim.x) s_begin[k] = lower_bound_u8(sorted_slot, E, k);
+tile_list_kernel(const uint32_t* __restrict__ sorted_key, long long E, int K, int num_blocks,
+                 long long* __restrict__ g_begin, int* __restrict__ g_tile0, int4* __restrict__ tiles,
+                 int* __restrict__ num_tiles) {
+    const int G = num_blocks * K;
+    for (int g = threadIdx.x; g <= G; g += blockDim.x) {
+        const uint32_t key = ((uint32_t)(g / K) << 8) | (uint32_t)(g % K);
+        g_begin[g] = g == G ? E : lower_bound_u32(sorted_key, E, key);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         int t = 0;
-        for (int k = 0; k < K; ++k) {
-            s_tile0[k] = t;
-            t += (int)((s_begin[k + 1] - s_begin[k] + TM - 1) / TM);
+        for (int g = 0; g < G; ++g) {
+            g_tile0[g] = t;
+            t += (int)((g_begin[g + 1] - g_begin[g] + TM - 1) / TM);
         }
-        s_tile0[K] = t;
+        g_tile0[G] = t;
         *num_tiles = t;
     }
     __syncthreads();
-    for (int k = threadIdx.x; k <= K; k += blockDim.x) slot_begin[k] = (int)s_begin[k];
-    for (int k = 0; k < K; ++k) {
-        const int nt = s_tile0[k + 1] - s_tile0[k];
+    for (int g = 0; g < G; ++g) {
+        const int nt = g_tile0[g + 1] - g_tile0[g];
         for (int i = threadIdx.x; i < nt; i += blockDim.x) {
-            const long long start = s_begin[k] + (long long)i * TM;
-            const int cnt = (int)min((long long)TM, s_begin[k + 1] - start);
-            tiles[s_tile0[k] + i] = make_int4(k, (int)start, cnt, 0);
+            const long long start = g_begin[g] + (long long)i * TM;
+            const int cnt = (int)min((long long)TM, g_begin[g + 1] - start);
+            tiles[g_tile0[g] + i] = make_int4(g % K, (int)start, cnt, 0);
         }
     }
 }
@@ -111,30 +121,36 @@ void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, c
                      int64_t E, int K, cudaStream_t s) {
     ASRB_REQUIRE(K >= 1 && K <= 256, "sparse_conv: kernel_size must be in [1, 256]");
     ASRB_REQUIRE(E < (int64_t(1) << 31), "sparse_conv: too many neighbour entries");
+    ASRB_REQUIRE(V_out < (int64_t(1) << 31), "sparse_conv: too many output rows");
     P.V_out = V_out;
     P.E = E;
     P.K = K;
-    P.max_tiles = (int)((E + TM - 1) / TM) + K;
+    const int num_blocks = (int)((V_out + (int64_t(1) << kRowBlockShift) - 1) >> kRowBlockShift);
+    const int G = std::max(num_blocks, 1) * K;
+    P.max_tiles = (int)((E + TM - 1) / TM) + G;
     P.p_in.alloc((size_t)E, s);
     P.p_out.alloc((size_t)E, s);
     P.perm.alloc((size_t)E, s);
     P.tiles.alloc((size_t)P.max_tiles, s);
     P.num_tiles.alloc(1, s);
-    P.slot_begin.alloc((size_t)K + 1, s);
     ProfileScope prof("conv_plan_build", s);
     DevBuf<uint32_t> rows((size_t)E, s);
-    DevBuf<uint8_t> keys((size_t)E, s);
+    DevBuf<uint32_t> keys((size_t)E, s);
+    DevBuf<long long> g_begin((size_t)G + 1, s);
+    DevBuf<int> g_tile0((size_t)G + 1, s);
     if (E) {
         entry_rows_kernel<<<grid_for((size_t)V_out * 8, 256), 256, 0, s>>>(d_splits, V_out, d_slot, rows.get(),
                                                                           keys.get(), P.perm.get());
         ASRB_CHECK_LAUNCH();
-        sort_pairs_u8_u32(keys.get(), P.perm.get(), (size_t)E, s, 8);
+        int bits = 8;
+        while (bits < 32 && (int64_t(1) << (bits - 8)) < std::max(num_blocks, 1)) ++bits;
+        sort_pairs_u32_u32(keys.get(), P.perm.get(), (size_t)E, s, bits);
         gather_pairs_kernel<<<grid_for(E, 256), 256, 0, s>>>(P.perm.get(), rows.get(), d_idx, E, P.p_in.get(),
                                                              P.p_out.get());
         ASRB_CHECK_LAUNCH();
     }
-    tile_list_kernel<<<1, 256, 0, s>>>(keys.get(), E, K, (int4*)P.tiles.get(), P.num_tiles.get(),
-                                       P.slot_begin.get());
+    tile_list_kernel<<<1, 256, 0, s>>>(keys.get(), E, K, std::max(num_blocks, 1), g_begin.get(), g_tile0.get(),
+                                       (int4*)P.tiles.get(), P.num_tiles.get());
     ASRB_CHECK_LAUNCH();
 }
 

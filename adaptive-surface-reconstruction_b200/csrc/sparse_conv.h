@@ -12,11 +12,10 @@ struct ConvPlan {
     int64_t V_out = 0, E = 0;
     int K = 0;
     int max_tiles = 0;
-    DevBuf<int32_t> p_in, p_out;  // [E] pairs sorted (stably) by kernel slot
+    DevBuf<int32_t> p_in, p_out;  // [E] pairs sorted (stably) by (row block, kernel slot)
     DevBuf<uint32_t> perm;        // [E] original CSR position of each sorted pair
     DevBuf<Int4Pod> tiles;        // (slot, first pair, count, -)
     DevBuf<int> num_tiles;        // device scalar
-    DevBuf<int> slot_begin;       // [K+1]
 };
 
 void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, const int64_t* d_splits, int64_t V_out,

@@ -1,0 +1,117 @@
+// Minimal tcgen05 / TMEM / mbarrier building blocks (inline PTX, sm_100a) for
+// the tensor-core contractions of this library.
+//
+// Operand layout used everywhere here: the *no-swizzle K-major canonical layout*:
+// an operand tile [R rows x 32 fp32] is stored as 8x(16 B) "core matrices"
+//     byte offset(r, k) = (r / 8) * SBO + (k / 4) * LBO + (r % 8) * 16 + (k % 4) * 4
+// with LBO = 128 (next core matrix along K) and SBO = 1024 (next 8 rows).
+// One tcgen05.mma.kind::tf32 consumes K = 8 (two core matrices along K).
+//
+// fp32 accuracy on the tf32 pipe: "3xTF32" — x = hi + lo with hi = x with the 13
+// low mantissa bits cleared (exactly representable in tf32) and lo = x - hi
+// (exact); D += A_hi B_hi + A_lo B_hi + A_hi B_lo; the dropped lo*lo term is
+// 2^-22 relative.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace asrb {
+namespace umma {
+
+constexpr uint32_t kLBO = 128;
+constexpr uint32_t kSBO = 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// byte offset of element (r, k) (k < 32) inside a K-major no-swizzle tile
+__device__ __forceinline__ uint32_t tile_offset(int r, int k) {
+    return (uint32_t)((r >> 3) * kSBO + (k >> 2) * kLBO + (r & 7) * 16 + (k & 3) * 4);
+}
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((kLBO >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((kSBO >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version for sm_100
+    return d;                // base offset 0, layout type 0 = no swizzle
+}
+
+// kind::tf32, fp32 accumulate, A and B K-major, M x N tile
+__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    const uint32_t acc = accumulate ? 1u : 0u;
+    asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+            "}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+            : "memory");
+}
+
+__device__ __forceinline__ void mma_commit(uint64_t* mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
+    const uint32_t a = smem_u32(mbar);
+    asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "WAIT_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+            "@p bra DONE_%=;\n\t"
+            "bra WAIT_%=;\n\t"
+            "DONE_%=:\n\t"
+            "}\n" ::"r"(a),
+            "r"(parity)
+            : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// whole warp; ncols power of two in [32, 512]; the TMEM base address lands in *slot (shared)
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread = its warp's TMEM lane, v[j] = column j
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr)
+            : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+}  // namespace umma
+}  // namespace asrb

@@ -91,11 +91,14 @@ int asr_duals_fill(asr_octree* tree, int64_t* d_dual_vertex_indices, void* strea
  * asr::ComputeAggregationNeighborsAndScaleCompatibility, cpp/lib/nsearch.h:72-80 /
  * nsearch.cpp:107-162 (python twin: o3d.core.nns multi_radius_search,
  * models/v0/datareader.py:776-785): per query all points with d^2 < r^2, ascending
- * by d^2 (ties by index); distances are SQUARED. */
+ * by d^2 (ties by index); distances are SQUARED.
+ * h_frame (may be NULL): {origin x, y, z, finest cell size} of the 2^21-per-axis binning grid;
+ * passing the octree's frame (asr_octree_get_frame: -offset*voxel_size[21], voxel_size[21]) makes
+ * the bins coincide with the voxels being queried (fewer candidates); results do not depend on it. */
 typedef struct asr_search asr_search;
 int asr_radius_search_create(const float* d_points, int64_t num_points, const float* d_queries,
-                             const float* d_radii, int64_t num_queries, void* stream, asr_search** out,
-                             int64_t* num_pairs);
+                             const float* d_radii, int64_t num_queries, const float* h_frame, void* stream,
+                             asr_search** out, int64_t* num_pairs);
 int asr_radius_search_fill(asr_search* search, int32_t* d_neighbors_index, float* d_neighbors_dist,
                            int64_t* d_neighbors_row_splits, void* stream);
 void asr_radius_search_destroy(asr_search* search);
@@ -157,6 +160,18 @@ int asr_invert_neighbors_list(int64_t num_points, const int32_t* d_inp_neighbors
 int asr_decode(const float* d_shifts, const float* d_code, int64_t num_voxels, const float* d_w1, const float* d_b1,
                const float* d_w2, const float* d_b2, const float* d_w3, const float* d_signed_scale,
                float* d_values, float* d_grad, void* stream);
+
+/* ---------------------------------------------------------------- dense layer on tensor cores
+ * out[rows, out_features] = act(a[rows, in_features] @ w[in_features, out_features] + bias) on
+ * tcgen05.mma kind::tf32 with a 3xTF32 split (fp32-level accuracy), accumulators in TMEM.  The
+ * weight matrix ([in, out] row-major, i.e. torch.nn.Linear.weight.T) is packed once with
+ * asr_pack_weights into asr_packed_weights_size() floats.  out_features <= 256.  d_bias may be
+ * NULL; relu applies only with a bias.  Used for the decoder MLP layers
+ * (net_definitions_torch.py:503-511,655-666). */
+int64_t asr_packed_weights_size(int in_features, int out_features);
+int asr_pack_weights(const float* d_w, int in_features, int out_features, float* d_packed, void* stream);
+int asr_dense_tf32x3(const float* d_a, int64_t rows, int in_features, int lda, const float* d_packed_w,
+                     int out_features, const float* d_bias, int relu, float* d_out, int ldd, void* stream);
 
 /* ---------------------------------------------------------------- dual contouring (vertices)
  * replaces the vertex passes of asr::CreateTriangleMesh, cpp/lib/contouring.h:25-30 /
