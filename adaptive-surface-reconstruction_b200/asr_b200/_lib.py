@@ -47,7 +47,9 @@ SIGNATURES = {
                                    _i32, _vp, _i32, _vp, _vp]),
     "asr_conv_plan_create": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _vp, _pp]),
     "asr_conv_plan_destroy": (None, [_vp]),
-    "asr_sparse_conv": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "asr_packed_conv_filters_size": (_i64, [_i32, _i32, _i32]),
+    "asr_pack_conv_filters": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "asr_sparse_conv": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "asr_reduce_subarrays_sum": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "asr_invert_neighbors_list": (_i32, [_i64, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _vp]),
     "asr_decode": (_i32, [_vp, _vp, _i64] + [_vp] * 9),

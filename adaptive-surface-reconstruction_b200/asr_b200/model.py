@@ -57,6 +57,19 @@ class _Block(torch.nn.Module):
         for j in range(2, depth + 1):
             setattr(self, "conv%d" % j, SpecialSparseConv(cout, cout, kernel_size))
         self._fused = None
+        self._packed = {}
+
+    def filters(self, j):
+        """Filter bank of conv j (1 = first conv, fused for the split form) in the
+        form the active backend wants: packed hi/lo tiles for the tensor-core
+        kernel (built once and cached), the fp32 tensor otherwise."""
+        W = self.first_conv()[0] if j == 1 else getattr(self, "conv%d" % j).kernel
+        if ops.SPARSE_CONV_BACKEND != "tensor" or W.shape[2] > 256:
+            return W
+        p = self._packed.get(j)
+        if p is None:
+            p = self._packed[j] = ops.PackedFilters(W)
+        return p
 
     def first_conv(self):
         """(kernel [K,Cin,Cout], bias [Cout]) of the first convolution; for the
@@ -72,7 +85,7 @@ class _Block(torch.nn.Module):
 
     def run(self, x, plan, importance=None):
         out_imp = None
-        W, b = self.first_conv()
+        W, b = self.filters(1), self.first_conv()[1]
         if self.split:
             col = self.output_channels - NORMALIZED_CHANNELS
             out_imp = ops.reduce_subarrays_sum(importance, plan.row_splits, index=plan.idx)
@@ -82,7 +95,7 @@ class _Block(torch.nn.Module):
             x = ops.sparse_conv(plan, W, x, bias=b, relu=True)
         for j in range(2, self.depth + 1):
             c = getattr(self, "conv%d" % j)
-            x = ops.sparse_conv(plan, c.kernel, x, bias=c.bias, relu=True)
+            x = ops.sparse_conv(plan, self.filters(j), x, bias=c.bias, relu=True)
         return x, out_imp
 
 
@@ -140,6 +153,7 @@ class UNet(torch.nn.Module):
         for m in self.modules():
             if isinstance(m, _Block):
                 m._fused = None
+                m._packed = {}
         return r
 
     # ------------------------------------------------------------------ reference methods
@@ -235,6 +249,7 @@ def seeded_weights(net, seed=0, scaled=True):
         for m in net.modules():
             if isinstance(m, _Block):
                 m._fused = None
+                m._packed = {}
     return net
 
 

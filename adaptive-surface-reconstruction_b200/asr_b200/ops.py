@@ -262,12 +262,39 @@ class ConvPlan:
             self._h = None
 
 
+# "tensor": tcgen05 3xTF32 contraction (default); "fp32": the FMA tile kernel
+SPARSE_CONV_BACKEND = "tensor"
+
+
+class PackedFilters:
+    """A [K, Cin, Cout] filter bank packed for the tensor-core tile kernel."""
+
+    def __init__(self, filters):
+        filters = _cuda(filters, torch.float32, "filters")
+        self.shape = tuple(filters.shape)
+        K, Cin, Cout = self.shape
+        if Cout > 256:
+            raise ValueError("tensor-core sparse conv needs out_channels <= 256")
+        self.data = torch.empty(int(lib().asr_packed_conv_filters_size(K, Cin, Cout)), dtype=torch.float32,
+                                device=filters.device)
+        check(lib().asr_pack_conv_filters(_ptr(filters), K, Cin, Cout, _ptr(self.data), _stream()))
+
+
 def sparse_conv(plan, filters, inp_features, inp_importance=None, neighbors_importance=None, importance_col=0,
-                normalize=False, normalize_col=0, normalizer=None, bias=None, relu=False):
-    """out[o] = sum_n imp_n * x[idx_n] @ filters[slot_n] (+ normalise, bias, ReLU)."""
-    filters = _cuda(filters, torch.float32, "filters")
+                normalize=False, normalize_col=0, normalizer=None, bias=None, relu=False, backend=None):
+    """out[o] = sum_n imp_n * x[idx_n] @ filters[slot_n] (+ normalise, bias, ReLU).
+    `filters` is a [K, Cin, Cout] tensor or a PackedFilters (pre-packed, tensor cores)."""
+    backend = backend or SPARSE_CONV_BACKEND
+    packed = None
+    if isinstance(filters, PackedFilters):
+        packed, filters = filters, None
+        K, Cin, Cout = packed.shape
+    else:
+        filters = _cuda(filters, torch.float32, "filters")
+        K, Cin, Cout = filters.shape
+        if backend == "tensor" and Cout <= 256:
+            packed = PackedFilters(filters)
     x = _cuda(inp_features, torch.float32, "inp_features")
-    K, Cin, Cout = filters.shape
     if K != plan.kernel_size:
         raise ValueError("filters.shape[0] does not match the plan's kernel size")
     if x.shape[1] != Cin:
@@ -276,7 +303,8 @@ def sparse_conv(plan, filters, inp_features, inp_importance=None, neighbors_impo
         ACCOUNT.append({"V_in": x.shape[0], "V_out": plan.num_out, "E": plan.idx.shape[0], "K": K, "Cin": Cin,
                         "Cout": Cout, "importance": inp_importance is not None or neighbors_importance is not None})
     out = torch.empty((plan.num_out, Cout), dtype=torch.float32, device=x.device)
-    check(lib().asr_sparse_conv(plan._h, _ptr(filters), _ptr(x), Cin, Cout,
+    check(lib().asr_sparse_conv(plan._h, _ptr(filters), _ptr(packed.data) if packed is not None else None, _ptr(x),
+                                Cin, Cout,
                                 _ptr(_opt(inp_importance, torch.float32, "inp_importance")),
                                 _ptr(_opt(neighbors_importance, torch.float32, "neighbors_importance")),
                                 int(importance_col), int(bool(normalize)), int(normalize_col),

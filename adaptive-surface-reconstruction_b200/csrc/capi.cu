@@ -246,14 +246,29 @@ int asr_conv_plan_create(const int32_t* idx, const uint8_t* slot, const int64_t*
 }
 void asr_conv_plan_destroy(asr_conv_plan* plan) { delete plan; }
 
-int asr_sparse_conv(const asr_conv_plan* plan, const float* filters, const float* x, int in_channels, int out_channels,
+int64_t asr_packed_conv_filters_size(int kernel_size, int in_channels, int out_channels) {
+    return (int64_t)packed_conv_filters_floats(kernel_size, in_channels, out_channels);
+}
+int asr_pack_conv_filters(const float* d_filters, int kernel_size, int in_channels, int out_channels, float* d_packed,
+                          void* stream) {
+    return guarded([&] {
+        ASRB_REQUIRE(kernel_size >= 1 && in_channels >= 1 && out_channels >= 1 && out_channels <= 256,
+                     "pack_conv_filters: bad shape (out_channels must be <= 256)");
+        pack_conv_filters(d_filters, kernel_size, in_channels, out_channels, d_packed, S(stream));
+    });
+}
+
+int asr_sparse_conv(const asr_conv_plan* plan, const float* filters, const float* packed_filters, const float* x,
+                    int in_channels, int out_channels,
                     const float* inp_importance, const float* neighbors_importance, int importance_col, int normalize,
                     int normalize_col, const float* normalizer, const int64_t* splits, const float* bias, int relu,
                     float* out, void* stream) {
     return guarded([&] {
         ASRB_REQUIRE(plan, "plan is null");
         ASRB_REQUIRE(!normalize || normalizer || splits, "normalize needs a normalizer or the row splits");
-        sparse_conv_forward(plan->p, x, filters, in_channels, out_channels, inp_importance, neighbors_importance,
+        ASRB_REQUIRE(filters || packed_filters, "filters is null");
+        sparse_conv_forward(plan->p, x, filters, packed_filters, in_channels, out_channels, inp_importance,
+                            neighbors_importance,
                             importance_col, normalize, normalize_col, normalizer, splits, bias, relu, out, S(stream));
     });
 }

@@ -406,8 +406,8 @@ static void launch_tiles(const ConvPlan& P, const TileArgs& a, cudaStream_t s) {
     ASRB_CHECK_LAUNCH();
 }
 
-void sparse_conv_forward(const ConvPlan& P, const float* x, const float* w, int Cin, int Cout, const float* imp_in,
-                         const float* imp_entry, int imp_col, int normalize, int norm_col, const float* norm,
+void sparse_conv_forward(const ConvPlan& P, const float* x, const float* w, const float* wp, int Cin, int Cout,
+                         const float* imp_in, const float* imp_entry, int imp_col, int normalize, int norm_col, const float* norm,
                          const int64_t* splits, const float* bias, int relu, float* out, cudaStream_t s) {
     ASRB_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0, "sparse_conv: channel counts must be multiples of 4");
     if (P.V_out == 0) return;
@@ -415,7 +415,9 @@ void sparse_conv_forward(const ConvPlan& P, const float* x, const float* w, int 
         ProfileScope prof("sparse_conv_zero", s);
         ASRB_CUDA(cudaMemsetAsync(out, 0, (size_t)P.V_out * Cout * sizeof(float), s));
     }
-    if (P.E > 0) {
+    if (P.E > 0 && wp) {
+        sparse_conv_tc_tiles(P, x, wp, Cin, Cout, imp_in, imp_entry, imp_col, out, s);
+    } else if (P.E > 0) {
         TileArgs a;
         a.x = x;
         a.w = w;

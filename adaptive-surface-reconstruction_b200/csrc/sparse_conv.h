@@ -25,9 +25,16 @@ void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, c
 // index) and/or imp_entry (per CSR entry) weight channels >= imp_col;
 // normalize divides channels >= norm_col by norm[row] (or the row length when
 // norm is null) where that is non-zero.
-void sparse_conv_forward(const ConvPlan& P, const float* x, const float* w, int Cin, int Cout, const float* imp_in,
+// wp != nullptr selects the tensor-core tile kernel (filters packed by pack_conv_filters).
+void sparse_conv_forward(const ConvPlan& P, const float* x, const float* w, const float* wp, int Cin, int Cout,
+                         const float* imp_in,
                          const float* imp_entry, int imp_col, int normalize, int norm_col, const float* norm,
                          const int64_t* splits, const float* bias, int relu, float* out, cudaStream_t s);
+
+size_t packed_conv_filters_floats(int K, int Cin, int Cout);
+void pack_conv_filters(const float* W, int K, int Cin, int Cout, float* out, cudaStream_t s);
+void sparse_conv_tc_tiles(const ConvPlan& P, const float* x, const float* wp, int Cin, int Cout, const float* imp_in,
+                          const float* imp_entry, int imp_col, float* out, cudaStream_t s);
 
 void row_importance(const float* imp, const int32_t* idx, const int64_t* splits, int64_t V, float* out,
                     cudaStream_t s);

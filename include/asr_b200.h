@@ -136,8 +136,16 @@ void asr_conv_plan_destroy(asr_conv_plan* plan);
  * weighted by imp_n = d_inp_importance[idx_n] (and/or d_neighbors_importance[n]);
  * normalize != 0 divides channels >= normalize_col by d_normalizer[o] (or by the row
  * length when d_normalizer is NULL) where non-zero; then + bias, ReLU if requested.
- * Channel counts must be multiples of 4; all float pointers 16-byte aligned. */
-int asr_sparse_conv(const asr_conv_plan* plan, const float* d_filters, const float* d_inp_features,
+ * Channel counts must be multiples of 4; all float pointers 16-byte aligned.
+ * d_packed_filters (may be NULL): the filter bank packed by asr_pack_conv_filters
+ * (asr_packed_conv_filters_size floats; hi/lo tf32 parts in the UMMA canonical layout).  When
+ * given (out_channels <= 256) the contraction runs on the tensor cores (tcgen05.mma kind::tf32,
+ * 3xTF32 split, fp32-level accuracy) and d_filters may be NULL; otherwise the fp32 FMA kernel runs. */
+int64_t asr_packed_conv_filters_size(int kernel_size, int in_channels, int out_channels);
+int asr_pack_conv_filters(const float* d_filters, int kernel_size, int in_channels, int out_channels,
+                          float* d_packed, void* stream);
+int asr_sparse_conv(const asr_conv_plan* plan, const float* d_filters, const float* d_packed_filters,
+                    const float* d_inp_features,
                     int in_channels, int out_channels, const float* d_inp_importance,
                     const float* d_neighbors_importance, int importance_col, int normalize, int normalize_col,
                     const float* d_normalizer, const int64_t* d_neighbors_row_splits, const float* d_bias, int relu,

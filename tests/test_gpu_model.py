@@ -18,9 +18,11 @@ def _load(levels, stress, seed=0):
     return P, net
 
 
-@pytest.mark.parametrize("levels,stress", [(5, True), (5, False), (3, True), (6, True)])
-def test_network_matches_oracle(levels, stress):
-    from asr_b200 import clouds, pipeline
+@pytest.mark.parametrize("levels,stress,backend", [(5, True, "tensor"), (5, False, "tensor"), (3, True, "tensor"),
+                                                   (6, True, "tensor"), (5, True, "fp32")])
+def test_network_matches_oracle(levels, stress, backend, monkeypatch):
+    from asr_b200 import clouds, ops, pipeline
+    monkeypatch.setattr(ops, "SPARSE_CONV_BACKEND", backend)
     from oracle import pipeline_cpu
     c = clouds.adaptive_blob(20000, seed=2) if levels != 6 else clouds.thingi_like(40000, seed=2)
     P, net = _load(levels, stress)
@@ -39,7 +41,14 @@ def test_network_matches_oracle(levels, stress):
     assert (imp.cpu().double() - rimp.double()).abs().max() <= 1e-6
     code = net.unet((feats, imp), d)
     rcode = model_cpu.unet(P, (rfeats, rimp), rd, levels, dtype=torch.float64)
-    assert (code.cpu().double() - rcode).abs().max() <= TOL
+    # The U-Net code is an intermediate feature tensor whose magnitude depends on the (random)
+    # weights — up to ~40 with the stress initialiser — so it is compared relative to its scale:
+    # 1e-4 of max|code| on the tensor-core backend (3xTF32, whose accumulator truncates, see
+    # sparse_conv_tc.cu), 1e-5 on the fp32 FMA backend.  The SDF output below is O(1) and keeps
+    # the absolute 1e-4 bar of the north star.
+    scale = max(1.0, rcode.abs().max().item())
+    rel = 1e-4 if backend == "tensor" else 1e-5
+    assert (code.cpu().double() - rcode).abs().max() <= rel * scale
     if stress:
         assert rcode.abs().max() > 1e-2  # the comparison is not vacuous
     assert (out["values"].cpu().double() - ref["values"]).abs().max() <= TOL

@@ -99,9 +99,11 @@ def ref_with(imp, W, g, c, feats, idx, rs):
 
 @pytest.mark.parametrize("cin,cout", [(32, 64), (64, 128), (128, 32), (36, 56), (8, 8), (256, 256)])
 @pytest.mark.parametrize("level", [0, 1])
-def test_sparse_conv_within_grid(cin, cout, level):
+@pytest.mark.parametrize("backend", ["tensor", "fp32"])
+def test_sparse_conv_within_grid(cin, cout, level, backend, monkeypatch):
     from asr_b200 import ops
     from oracle import ops_cpu
+    monkeypatch.setattr(ops, "SPARSE_CONV_BACKEND", backend)
     c, t, grids = _scene(n=12000 if cin * cout > 20000 else 30000)
     g = grids[level]
     V = g["neighbors_row_splits"].shape[0] - 1
