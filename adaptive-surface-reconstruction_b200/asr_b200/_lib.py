@@ -109,8 +109,8 @@ def profile_read():
     L = lib()
     out = {}
     for i in range(L.asr_profile_count()):
-        name = C.create_string_buffer(64)
+        name = C.create_string_buffer(128)
         ms, fl, n = C.c_double(0), C.c_double(0), C.c_int64(0)
-        if L.asr_profile_get(i, name, 64, C.byref(ms), C.byref(n), C.byref(fl)) == 0:
+        if L.asr_profile_get(i, name, 128, C.byref(ms), C.byref(n), C.byref(fl)) == 0:
             out[name.value.decode()] = {"ms": ms.value, "launches": n.value, "flops": fl.value}
     return out

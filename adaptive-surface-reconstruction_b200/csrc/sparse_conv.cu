@@ -401,7 +401,9 @@ static void launch_tiles(const ConvPlan& P, const TileArgs& a, cudaStream_t s) {
         configured = true;
     }
     dim3 grid((unsigned)P.max_tiles, (unsigned)((a.Cout + TN - 1) / TN));
-    ProfileScope prof("sparse_conv_tile", s, 2.0 * (double)P.E * a.Cin * a.Cout);
+    char label[96];
+    snprintf(label, sizeof(label), "sparse_conv_tile/fp32 K%d %dx%d E%lld", P.K, a.Cin, a.Cout, (long long)P.E);
+    ProfileScope prof(label, s, 2.0 * (double)P.E * a.Cin * a.Cout);
     sparse_conv_tile_kernel<TN><<<grid, kThreads, smem, s>>>(a);
     ASRB_CHECK_LAUNCH();
 }
