@@ -59,16 +59,16 @@ class _Block(torch.nn.Module):
         self._fused = None
         self._packed = {}
 
-    def filters(self, j):
+    def filters(self, j, K=ops):
         """Filter bank of conv j (1 = first conv, fused for the split form) in the
         form the active backend wants: packed hi/lo tiles for the tensor-core
         kernel (built once and cached), the fp32 tensor otherwise."""
         W = self.first_conv()[0] if j == 1 else getattr(self, "conv%d" % j).kernel
-        if ops.SPARSE_CONV_BACKEND != "tensor" or W.shape[2] > 256:
+        if getattr(K, "PackedFilters", None) is None or K.SPARSE_CONV_BACKEND != "tensor" or W.shape[2] > 256:
             return W
         p = self._packed.get(j)
         if p is None:
-            p = self._packed[j] = ops.PackedFilters(W)
+            p = self._packed[j] = K.PackedFilters(W)
         return p
 
     def first_conv(self):
@@ -83,19 +83,20 @@ class _Block(torch.nn.Module):
                                torch.cat([self.conv1a.bias, self.conv1b.bias]).contiguous())
         return self._fused
 
-    def run(self, x, plan, importance=None):
+    def run(self, x, plan, importance=None, K=ops):
+        """K = kernel namespace: asr_b200.ops, or shard.ShardedOps for multi-GPU."""
         out_imp = None
-        W, b = self.filters(1), self.first_conv()[1]
+        W, b = self.filters(1, K), self.first_conv()[1]
         if self.split:
             col = self.output_channels - NORMALIZED_CHANNELS
-            out_imp = ops.reduce_subarrays_sum(importance, plan.row_splits, index=plan.idx)
-            x = ops.sparse_conv(plan, W, x, inp_importance=importance, importance_col=col, normalize=True,
-                                normalize_col=col, normalizer=out_imp, bias=b, relu=True)
+            out_imp = K.reduce_subarrays_sum(importance, plan.row_splits, index=plan.idx)
+            x = K.sparse_conv(plan, W, x, inp_importance=importance, importance_col=col, normalize=True,
+                              normalize_col=col, normalizer=out_imp, bias=b, relu=True)
         else:
-            x = ops.sparse_conv(plan, W, x, bias=b, relu=True)
+            x = K.sparse_conv(plan, W, x, bias=b, relu=True)
         for j in range(2, self.depth + 1):
             c = getattr(self, "conv%d" % j)
-            x = ops.sparse_conv(plan, self.filters(j), x, bias=c.bias, relu=True)
+            x = K.sparse_conv(plan, self.filters(j, K), x, bias=c.bias, relu=True)
         return x, out_imp
 
 
@@ -144,6 +145,7 @@ class UNet(torch.nn.Module):
         self.dense_decoder2 = torch.nn.Linear(32, 32, bias=True)
         self.dense_decoder3 = torch.nn.Linear(32, 2, bias=False)
         self.requires_grad_(False)
+        self.K = ops  # kernel namespace; shard.ShardedOps(ops, group) for the multi-GPU path
 
     def _down(self, level):
         return getattr(self, "sparseconv_down%d" % min(level, 3))
@@ -159,13 +161,13 @@ class UNet(torch.nn.Module):
     # ------------------------------------------------------------------ reference methods
     def aggregate(self, input_dict):
         """UNet5.aggregate (:640-653) -> (feats [V0,32], per-PAIR importance [P])."""
-        d = input_dict
-        imp = ops.aggregation_importance(d["aggregation_scale_compat"], d["aggregation_neighbors_dist"])
+        d, K = input_dict, self.K
+        imp = K.aggregation_importance(d["aggregation_scale_compat"], d["aggregation_neighbors_dist"])
         c = self.cconv_block_in.conv1
-        feats = ops.continuous_conv(c.kernel, d["voxel_centers0"], d["voxel_sizes0"], c.offset, d["points"],
-                                    d["feats"], None, d["aggregation_neighbors_index"], imp,
-                                    d["aggregation_row_splits"], normalize=True, bias=c.bias, relu=True)
-        return feats, imp
+        feats = K.continuous_conv(c.kernel, d["voxel_centers0"], d["voxel_sizes0"], c.offset, d["points"],
+                                  d["feats"], None, d["aggregation_neighbors_index"], imp,
+                                  d["aggregation_row_splits"], normalize=True, bias=c.bias, relu=True)
+        return feats, K.pair_importance_for_unet(imp, d["voxel_centers0"].shape[0])
 
     def plans(self, input_dict):
         """Slot-sorted conv plans of all neighbour tables, cached in the dict."""
@@ -173,36 +175,36 @@ class UNet(torch.nn.Module):
         if cache is not None:
             return cache
         L = self.octree_levels
-        d = input_dict
+        d, K = input_dict, self.K
         P = {"nb": [], "up": [], "down": []}
         for i in range(L):
-            P["nb"].append(ops.ConvPlan(d["neighbors_index%d" % i], d["neighbors_kernel_index%d" % i],
-                                        d["neighbors_row_splits%d" % i], 55))
+            P["nb"].append(K.ConvPlan(d["neighbors_index%d" % i], d["neighbors_kernel_index%d" % i],
+                                      d["neighbors_row_splits%d" % i], 55))
         for i in range(L - 1):
             ui, uk, us = (d["up_neighbors_index%d" % i], d["up_neighbors_kernel_index%d" % i],
                           d["up_neighbors_row_splits%d" % i])
-            P["up"].append(ops.ConvPlan(ui, uk, us, 9))
-            inv = ops.invert_neighbors_list(d["voxel_centers%d" % (i + 1)].shape[0], ui, us, uk)
-            P["down"].append(ops.ConvPlan(inv.neighbors_index, inv.neighbors_attributes, inv.neighbors_row_splits, 9))
+            P["up"].append(K.ConvPlan(ui, uk, us, 9))
+            inv = K.invert_neighbors_list(d["voxel_centers%d" % (i + 1)].shape[0], ui, us, uk)
+            P["down"].append(K.ConvPlan(inv.neighbors_index, inv.neighbors_attributes, inv.neighbors_row_splits, 9))
         input_dict["_asr_plans"] = P
         return P
 
     def unet(self, feats1, input_dict):
         """UNet5.unet (:535-638)."""
-        L = self.octree_levels
+        L, K = self.octree_levels, self.K
         P = self.plans(input_dict)
         x, imp = feats1
         skips = []
-        x, imp = self.sparseconv_encblock0.run(x, P["nb"][0], imp)
+        x, imp = self.sparseconv_encblock0.run(x, P["nb"][0], imp, K)
         skips.append(x)
         for l in range(1, L):
-            x, imp = self._down(l).run(x, P["down"][l - 1], imp)
-            x, imp = getattr(self, "sparseconv_encblock%d" % l).run(x, P["nb"][l], imp)
+            x, imp = self._down(l).run(x, P["down"][l - 1], imp, K)
+            x, imp = getattr(self, "sparseconv_encblock%d" % l).run(x, P["nb"][l], imp, K)
             skips.append(x)
         for l in range(L - 2, -1, -1):
-            x, _ = getattr(self, "sparseconv_up%d" % l).run(x, P["up"][l])
+            x, _ = getattr(self, "sparseconv_up%d" % l).run(x, P["up"][l], None, K)
             x = torch.cat([x, skips[l]], -1) if l >= 1 else x + skips[0]
-            x, _ = getattr(self, "sparseconv_decblock%d" % l).run(x, P["nb"][l])
+            x, _ = getattr(self, "sparseconv_decblock%d" % l).run(x, P["nb"][l], None, K)
         return x
 
     def _decoder(self):
@@ -211,11 +213,11 @@ class UNet(torch.nn.Module):
 
     def decode(self, shifts, code, signed_scale=None):
         """UNet5.decode (:655-666); signed_scale fuses asr.cpp:334-336."""
-        return ops.decode(shifts, code, *self._decoder(), signed_scale=signed_scale)
+        return self.K.decode(shifts, code, *self._decoder(), signed_scale=signed_scale)
 
     def decode_with_gradient(self, shifts, code):
         """UNet5.decode_with_gradient (:668-686)."""
-        return ops.decode(shifts, code, *self._decoder(), with_gradient=True)
+        return self.K.decode(shifts, code, *self._decoder(), with_gradient=True)
 
 
 def UNet5():

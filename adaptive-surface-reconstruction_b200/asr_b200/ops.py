@@ -207,9 +207,24 @@ def aggregation_importance(scale_compat, dist):
 # ------------------------------------------------------------------------------------ convolutions
 
 
+def _out_buffer(out, rows, cols, device):
+    if out is None:
+        return torch.empty((rows, cols), dtype=torch.float32, device=device)
+    if (not out.is_cuda or out.dtype != torch.float32 or tuple(out.shape) != (rows, cols) or not out.is_contiguous()
+            or out.data_ptr() % 16):
+        raise ValueError("out must be a contiguous 16-byte aligned CUDA float32 tensor of shape [%d, %d]" % (rows, cols))
+    return out
+
+
+def pair_importance_for_unet(importance, num_voxels):
+    """Identity on one GPU; the sharded namespace (shard.ShardedOps) assembles the
+    first `num_voxels` entries of the global pair list here."""
+    return importance
+
+
 def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_features, inp_importance,
                     neighbors_index, neighbors_importance, neighbors_row_splits, normalize=True, bias=None,
-                    relu=False):
+                    relu=False, out=None):
     filters = _cuda(filters, torch.float32, "filters")
     if filters.ndim != 5 or not (filters.shape[0] == filters.shape[1] == filters.shape[2]):
         raise ValueError("filters must have shape [S,S,S,Cin,Cout]")
@@ -227,7 +242,7 @@ def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_
     rs = _cuda(neighbors_row_splits, torch.int64, "neighbors_row_splits")
     if rs.shape[0] != V + 1:
         raise ValueError("neighbors_row_splits must have num_out+1 elements")
-    out = torch.empty((V, Cout), dtype=torch.float32, device=filters.device)
+    out = _out_buffer(out, V, Cout, filters.device)
     check(lib().asr_continuous_conv(
         _ptr(filters), _ptr(out_positions), _ptr(extents), 1 if extents.numel() == V and V != 1 else 0,
         _ptr(_opt(offset, torch.float32, "offset")), _ptr(inp_positions), _ptr(inp_features),
@@ -281,7 +296,7 @@ class PackedFilters:
 
 
 def sparse_conv(plan, filters, inp_features, inp_importance=None, neighbors_importance=None, importance_col=0,
-                normalize=False, normalize_col=0, normalizer=None, bias=None, relu=False, backend=None):
+                normalize=False, normalize_col=0, normalizer=None, bias=None, relu=False, backend=None, out=None):
     """out[o] = sum_n imp_n * x[idx_n] @ filters[slot_n] (+ normalise, bias, ReLU).
     `filters` is a [K, Cin, Cout] tensor or a PackedFilters (pre-packed, tensor cores)."""
     backend = backend or SPARSE_CONV_BACKEND
@@ -302,7 +317,7 @@ def sparse_conv(plan, filters, inp_features, inp_importance=None, neighbors_impo
     if ACCOUNT is not None:
         ACCOUNT.append({"V_in": x.shape[0], "V_out": plan.num_out, "E": plan.idx.shape[0], "K": K, "Cin": Cin,
                         "Cout": Cout, "importance": inp_importance is not None or neighbors_importance is not None})
-    out = torch.empty((plan.num_out, Cout), dtype=torch.float32, device=x.device)
+    out = _out_buffer(out, plan.num_out, Cout, x.device)
     check(lib().asr_sparse_conv(plan._h, _ptr(filters), _ptr(packed.data) if packed is not None else None, _ptr(x),
                                 Cin, Cout,
                                 _ptr(_opt(inp_importance, torch.float32, "inp_importance")),

@@ -35,12 +35,14 @@ class StageTimer:
             self._t = now
 
 
-def build_input_dict(points, normals, radii, bb_min, bb_max, levels=5, radius_scale=1.0, max_depth=21, timer=None):
+def build_input_dict(points, normals, radii, bb_min, bb_max, levels=5, radius_scale=1.0, max_depth=21, timer=None,
+                     K=ops):
     """Grid building + aggregation search (asr.cpp:143-312).  Returns
-    (input_dict, dual_vertex_indices, octree)."""
+    (input_dict, dual_vertex_indices, octree).  K = kernel namespace (ops or
+    shard.ShardedOps: there the aggregation arrays cover this rank's voxels)."""
     timer = timer or StageTimer()
     timer.start()
-    tree = ops.Octree(points, radii, bb_min, bb_max, radius_scale, 0, max_depth)
+    tree = K.Octree(points, radii, bb_min, bb_max, radius_scale, 0, max_depth)
     timer.lap("octree")
     duals = tree.dual_vertex_indices()
     timer.lap("duals")
@@ -55,11 +57,11 @@ def build_input_dict(points, normals, radii, bb_min, bb_max, levels=5, radius_sc
     if "voxel_centers0" not in d:  # empty tree
         d["voxel_centers0"] = torch.zeros((0, 3), dtype=torch.float32, device=points.device)
         d["voxel_sizes0"] = torch.zeros(0, dtype=torch.float32, device=points.device)
-    idx, dist, rs = ops.multi_radius_search(points, d["voxel_centers0"], d["voxel_sizes0"], frame=tree.search_frame())
+    idx, dist, rs = K.multi_radius_search(points, d["voxel_centers0"], d["voxel_sizes0"], frame=tree.search_frame())
     d["aggregation_neighbors_index"] = idx
     d["aggregation_neighbors_dist"] = dist
     d["aggregation_row_splits"] = rs
-    d["aggregation_scale_compat"] = ops.scale_compatibility(d["voxel_sizes0"], radii, idx, rs)
+    d["aggregation_scale_compat"] = K.scale_compatibility(d["voxel_sizes0"], radii, idx, rs)
     timer.lap("search")
     return d, duals, tree
 
@@ -87,10 +89,11 @@ def reconstruct_vertices(model, points, normals, radii, bb_min=None, bb_max=None
     if bb_min is None:
         bb_min = points.min(0).values.cpu().numpy()
         bb_max = points.max(0).values.cpu().numpy()
-    d, duals, tree = build_input_dict(points, normals, radii, bb_min, bb_max, levels, radius_scale, max_depth, timer)
+    K = getattr(model, "K", ops)
+    d, duals, tree = build_input_dict(points, normals, radii, bb_min, bb_max, levels, radius_scale, max_depth, timer, K)
     values = run_network(model, d, timer)
     timer.start()
-    verts, vdual = ops.contour_vertices(values, duals, d["voxel_centers0"], contouring_value_threshold)
+    verts, vdual = K.contour_vertices(values, duals, d["voxel_centers0"], contouring_value_threshold)
     timer.lap("contour")
     return {"vertices": verts, "vertex_dual": vdual, "values": values, "dual_vertex_indices": duals,
             "input_dict": d, "octree": tree}

@@ -194,27 +194,37 @@ sparse_conv_tc_kernel(TcArgs a) {
         // ------------------------------------------------------------ epilogue
         umma::mbar_wait(&mbar_acc, 0);
         umma::tc_fence_after();
-        const int o = s_out[tid];
-        const float imp = s_imp[tid];
-        float* orow = a.out + (size_t)(o < 0 ? 0 : o) * a.Cout;
+        // TMEM -> registers (thread = row) -> per-warp transpose through shared memory (the
+        // pipeline stages are idle now) so that each RED instruction of a warp covers 4 rows x
+        // 128 contiguous bytes (full 32-byte sectors) instead of 32 rows x 16 bytes.
+        float* T = reinterpret_cast<float*>(smem) + (size_t)warp * 32 * 36;  // [32 rows][36] per warp
+        const int lane = tid & 31;
         for (int n0 = 0; n0 < a.n_pad; n0 += 32) {
             float acc[32], cor[32];
             umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + n0, acc);
             umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + a.n_pad + n0, cor);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] += cor[j];
-            if (o >= 0) {
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(T + lane * 36 + j) =
+                        make_float4(acc[j] + cor[j], acc[j + 1] + cor[j + 1], acc[j + 2] + cor[j + 2], acc[j + 3] + cor[j + 3]);
+            __syncwarp();
+            const int cg = lane & 7;
+            const int n = n0 + cg * 4;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const int n = n0 + j;
-                    if (n < a.Cout) {
-                        float e[4];
+            for (int it = 0; it < 8; ++it) {
+                const int rl = it * 4 + (lane >> 3);
+                const int o = s_out[warp * 32 + rl];
+                if (o >= 0 && n < a.Cout) {
+                    const float imp = s_imp[warp * 32 + rl];
+                    const float4 t = *reinterpret_cast<const float4*>(T + rl * 36 + cg * 4);
+                    float e[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) e[q] = (n + q >= a.imp_col) ? acc[j + q] * imp : acc[j + q];
-                        red_add_v4(orow + n, e[0], e[1], e[2], e[3]);
-                    }
+                    for (int q = 0; q < 4; ++q)
+                        if (n + q >= a.imp_col) e[q] *= imp;
+                    red_add_v4(a.out + (size_t)o * a.Cout + n, e[0], e[1], e[2], e[3]);
                 }
             }
+            __syncwarp();
         }
     } else if ((tid & 31) == 0) {
         // ------------------------------------------------------------ MMA issuer

@@ -172,7 +172,7 @@ def run_gpu(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from asr_b200 import _lib, clouds, model, ops, pipeline
+    from asr_b200 import _lib, clouds, model, ops, pipeline, shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -186,9 +186,12 @@ def run_gpu(args):
     ops.SPARSE_CONV_BACKEND = args.backend
     peaks = load_peaks()
 
-    # replicas: every rank processes its own cloud of the named shape (weak scaling)
-    cloud = clouds.make(args.workload, args.points, seed=args.seed + rank)
+    # N > 1: ONE cloud, the path sharded by output-voxel ranges across the ranks with an all-gather
+    # of the produced rows after every sharded stage (asr_b200/shard.py) -> strong scaling
+    cloud = clouds.make(args.workload, args.points, seed=args.seed)
     net = model.seeded_weights(model.UNet(args.levels), seed=0).cuda()
+    if world > 1:
+        net.K = shard.ShardedOps(ops)
     host = {k: torch.from_numpy(cloud[k]).pin_memory() for k in ("points", "normals", "radii")}
     devt = {k: v.cuda() for k, v in host.items()}
     bb = (cloud["bb_min"], cloud["bb_max"])
@@ -258,13 +261,14 @@ def run_gpu(args):
     h2d = sum(t.numel() * t.element_size() for t in host.values())
     d2h = v.numel() * 4 + s.numel() * 4
 
+    total_steps = 1 + max(args.warmup - 1, 0) + args.steps + (1 if args.profile_run else args.steps + 1)
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e = t.tolist()
     ms_step, ms_step_e2e = ms_dev / args.steps, ms_e2e / args.steps
-    value = world * args.points / (ms_step * 1e-3)
-    e2e_value = world * args.points / (ms_step_e2e * 1e-3)
+    value = args.points / (ms_step * 1e-3)
+    e2e_value = args.points / (ms_step_e2e * 1e-3)
 
     if rank == 0:
         bytes_by_stage = algorithmic_bytes(sizes, convs)
@@ -305,10 +309,14 @@ def run_gpu(args):
                    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f32 (3xTF32 on tcgen05 for the sparse convs)" if ops.SPARSE_CONV_BACKEND == "tensor" else "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(args), "sparse_conv_backend": ops.SPARSE_CONV_BACKEND, "parallelism": "replicas x%d" % world if world > 1 else "1 gpu",
+            "config": {"workload": workload_name(args), "sparse_conv_backend": ops.SPARSE_CONV_BACKEND, "parallelism": ("%d gpus: geometry replicated, search/conv/decode sharded by output-voxel ranges, "
+                                       "all-gather of output rows per sharded stage (%d collectives, %.2f GB gathered per step)"
+                                       % (world, net.K.collectives // max(total_steps, 1),
+                                          net.K.bytes_gathered / max(total_steps, 1) / 1e9)) if world > 1 else "1 gpu",
                        "l2_policy": "inputs and every intermediate tensor larger than the 126 MB L2",
                        "sizes": sizes},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
