@@ -22,6 +22,7 @@ SIGNATURES = {
     "asr_version": (_i32, []),
     "asr_last_error": (C.c_char_p, []),
     "asr_kernel_launches": (_i64, []),
+    "asr_set_option": (_i32, [C.c_char_p, _i32]),
     "asr_profile_enable": (None, [_i32]),
     "asr_profile_reset": (None, []),
     "asr_profile_count": (_i32, []),
@@ -94,6 +95,10 @@ def check(rc):
 
 def kernel_launches():
     return int(lib().asr_kernel_launches())
+
+
+def set_option(name, value):
+    check(lib().asr_set_option(name.encode(), int(value)))
 
 
 def profile_enable(on=True):

@@ -85,6 +85,16 @@ int asr_version(void) { return ASR_B200_VERSION; }
 const char* asr_last_error(void) { return g_error.c_str(); }
 int64_t asr_kernel_launches(void) { return (int64_t)g_kernel_launches.load(); }
 
+int asr_set_option(const char* name, int value) {
+    return guarded([&] {
+        ASRB_REQUIRE(name != nullptr, "option name is null");
+        if (std::string(name) == "sparse_conv_output_stationary") sparse_conv_os_enable(value != 0);
+        else if (std::string(name) == "tc_stages") sparse_conv_tc_tune(value, 0);
+        else if (std::string(name) == "tc_row_groups") sparse_conv_tc_tune(0, value);
+        else throw Error(kInvalidArgument, std::string("unknown option: ") + name);
+    });
+}
+
 void asr_profile_enable(int on) { profile_set(on != 0); }
 void asr_profile_reset(void) { profile_reset(); }
 int asr_profile_count(void) { return profile_count(); }

@@ -87,38 +87,91 @@ __device__ __forceinline__ long long lower_bound_u32(const uint32_t* a, long lon
 }
 
 // one block: (row block, slot) run boundaries, then the tile list (slot, first pair, count)
+// for tiles of `tile_rows` pairs.  Prefix over the groups: per-thread chunks + a 256-entry scan.
 __global__ void __launch_bounds__(256)
-tile_list_kernel(const uint32_t* __restrict__ sorted_key, long long E, int K, int num_blocks,
+tile_list_kernel(const uint32_t* __restrict__ sorted_key, long long E, int K, int num_blocks, int tile_rows,
                  long long* __restrict__ g_begin, int* __restrict__ g_tile0, int4* __restrict__ tiles,
                  int* __restrict__ num_tiles) {
+    __shared__ int s_part[256];
     const int G = num_blocks * K;
     for (int g = threadIdx.x; g <= G; g += blockDim.x) {
         const uint32_t key = ((uint32_t)(g / K) << 8) | (uint32_t)(g % K);
         g_begin[g] = g == G ? E : lower_bound_u32(sorted_key, E, key);
     }
     __syncthreads();
+    const int chunk = (G + 255) / 256;
+    const int g0 = min(G, (int)threadIdx.x * chunk), g1 = min(G, g0 + chunk);
+    int sum = 0;
+    for (int g = g0; g < g1; ++g) sum += (int)((g_begin[g + 1] - g_begin[g] + tile_rows - 1) / tile_rows);
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
     if (threadIdx.x == 0) {
         int t = 0;
-        for (int g = 0; g < G; ++g) {
-            g_tile0[g] = t;
-            t += (int)((g_begin[g + 1] - g_begin[g] + TM - 1) / TM);
+        for (int i = 0; i < 256; ++i) {
+            const int v = s_part[i];
+            s_part[i] = t;
+            t += v;
         }
-        g_tile0[G] = t;
         *num_tiles = t;
     }
     __syncthreads();
-    for (int g = 0; g < G; ++g) {
-        const int nt = g_tile0[g + 1] - g_tile0[g];
-        for (int i = threadIdx.x; i < nt; i += blockDim.x) {
-            const long long start = g_begin[g] + (long long)i * TM;
-            const int cnt = (int)min((long long)TM, g_begin[g + 1] - start);
-            tiles[g_tile0[g] + i] = make_int4(g % K, (int)start, cnt, 0);
+    int t = s_part[threadIdx.x];
+    for (int g = g0; g < g1; ++g) {
+        const long long b = g_begin[g], e = g_begin[g + 1];
+        for (long long start = b; start < e; start += tile_rows)
+            tiles[t++] = make_int4(g % K, (int)start, (int)min((long long)tile_rows, e - start), 0);
+    }
+}
+
+constexpr int kCommonSlots = 7;  // self + 6 same-level face neighbours
+
+__global__ void __launch_bounds__(256)
+common_index_kernel(const int32_t* __restrict__ idx, const uint8_t* __restrict__ slot, const int64_t* __restrict__ splits,
+                    long long V, int32_t* __restrict__ cidx, int32_t* __restrict__ rare_count) {
+    long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    int c[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+    int rare = 0;
+    const int64_t e = splits[v + 1];
+    for (int64_t j = splits[v]; j < e; ++j) {
+        const int k = slot[j];
+        if (k < kCommonSlots) {
+            if (c[k] >= 0) ++rare;  // a duplicate slot within a row (never produced by the grid code): keep it pair-major
+            else c[k] = idx[j];
+        } else {
+            ++rare;
+        }
+    }
+    reinterpret_cast<int4*>(cidx)[2 * v] = make_int4(c[0], c[1], c[2], c[3]);
+    reinterpret_cast<int4*>(cidx)[2 * v + 1] = make_int4(c[4], c[5], c[6], c[7]);
+    rare_count[v] = rare;
+}
+
+__global__ void __launch_bounds__(256)
+rare_fill_kernel(const int32_t* __restrict__ idx, const uint8_t* __restrict__ slot, const int64_t* __restrict__ splits,
+                 long long V, const int64_t* __restrict__ rsplits, int32_t* __restrict__ ridx, uint8_t* __restrict__ rslot) {
+    long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    unsigned seen = 0;
+    int64_t o = rsplits[v];
+    const int64_t e = splits[v + 1];
+    for (int64_t j = splits[v]; j < e; ++j) {
+        const int k = slot[j];
+        bool rare = k >= kCommonSlots;
+        if (!rare) {
+            if (seen & (1u << k)) rare = true;
+            seen |= 1u << k;
+        }
+        if (rare) {
+            ridx[o] = idx[j];
+            rslot[o] = (uint8_t)k;
+            ++o;
         }
     }
 }
 
 void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, const int64_t* d_splits, int64_t V_out,
-                     int64_t E, int K, cudaStream_t s) {
+                     int64_t E, int K, cudaStream_t s, bool with_output_stationary) {
     ASRB_REQUIRE(K >= 1 && K <= 256, "sparse_conv: kernel_size must be in [1, 256]");
     ASRB_REQUIRE(E < (int64_t(1) << 31), "sparse_conv: too many neighbour entries");
     ASRB_REQUIRE(V_out < (int64_t(1) << 31), "sparse_conv: too many output rows");
@@ -128,6 +181,9 @@ void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, c
     const int num_blocks = (int)((V_out + (int64_t(1) << kRowBlockShift) - 1) >> kRowBlockShift);
     const int G = std::max(num_blocks, 1) * K;
     P.max_tiles = (int)((E + TM - 1) / TM) + G;
+    P.max_tiles2 = (int)((E + 2 * TM - 1) / (2 * TM)) + G;
+    P.tiles2.alloc((size_t)P.max_tiles2, s);
+    P.num_tiles2.alloc(1, s);
     P.p_in.alloc((size_t)E, s);
     P.p_out.alloc((size_t)E, s);
     P.perm.alloc((size_t)E, s);
@@ -149,9 +205,33 @@ void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, c
                                                              P.p_out.get());
         ASRB_CHECK_LAUNCH();
     }
-    tile_list_kernel<<<1, 256, 0, s>>>(keys.get(), E, K, std::max(num_blocks, 1), g_begin.get(), g_tile0.get(),
+    tile_list_kernel<<<1, 256, 0, s>>>(keys.get(), E, K, std::max(num_blocks, 1), TM, g_begin.get(), g_tile0.get(),
                                        (int4*)P.tiles.get(), P.num_tiles.get());
     ASRB_CHECK_LAUNCH();
+    tile_list_kernel<<<1, 256, 0, s>>>(keys.get(), E, K, std::max(num_blocks, 1), 2 * TM, g_begin.get(), g_tile0.get(),
+                                       (int4*)P.tiles2.get(), P.num_tiles2.get());
+    ASRB_CHECK_LAUNCH();
+
+    if (with_output_stationary && K == 55 && V_out > 0) {
+        P.cidx.alloc((size_t)V_out * 8, s);
+        DevBuf<int32_t> rare_count((size_t)V_out, s);
+        DevBuf<int64_t> rsplits((size_t)V_out + 1, s);
+        common_index_kernel<<<grid_for(V_out, 256), 256, 0, s>>>(d_idx, d_slot, d_splits, V_out, P.cidx.get(),
+                                                                 rare_count.get());
+        ASRB_CHECK_LAUNCH();
+        exclusive_sum_i32_to_i64(rare_count.get(), rsplits.get(), (size_t)V_out, s);
+        const int64_t E_rare = d2h_scalar(rsplits.get() + V_out, s);
+        P.E_common = E - E_rare;
+        DevBuf<int32_t> ridx((size_t)E_rare, s);
+        DevBuf<uint8_t> rslot((size_t)E_rare, s);
+        if (E_rare) {
+            rare_fill_kernel<<<grid_for(V_out, 256), 256, 0, s>>>(d_idx, d_slot, d_splits, V_out, rsplits.get(),
+                                                                  ridx.get(), rslot.get());
+            ASRB_CHECK_LAUNCH();
+        }
+        P.rare = std::make_unique<ConvPlan>();
+        conv_plan_build(*P.rare, ridx.get(), rslot.get(), rsplits.get(), V_out, E_rare, K, s, false);
+    }
 }
 
 // ------------------------------------------------------------------ tile kernel
@@ -413,6 +493,10 @@ void sparse_conv_forward(const ConvPlan& P, const float* x, const float* w, cons
                          const int64_t* splits, const float* bias, int relu, float* out, cudaStream_t s) {
     ASRB_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0, "sparse_conv: channel counts must be multiples of 4");
     if (P.V_out == 0) return;
+    if (wp && !imp_in && !imp_entry && !normalize && sparse_conv_os_supported(P, Cin, Cout)) {
+        sparse_conv_os(P, x, wp, Cin, Cout, bias, relu, out, s);
+        return;
+    }
     {
         ProfileScope prof("sparse_conv_zero", s);
         ASRB_CUDA(cudaMemsetAsync(out, 0, (size_t)P.V_out * Cout * sizeof(float), s));

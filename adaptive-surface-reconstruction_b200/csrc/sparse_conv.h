@@ -1,4 +1,6 @@
 #pragma once
+#include <memory>
+
 #include "common.cuh"
 
 namespace asrb {
@@ -16,10 +18,19 @@ struct ConvPlan {
     DevBuf<uint32_t> perm;        // [E] original CSR position of each sorted pair
     DevBuf<Int4Pod> tiles;        // (slot, first pair, count, -)
     DevBuf<int> num_tiles;        // device scalar
+    int max_tiles2 = 0;           // same for 256-pair tiles (tensor-core kernel, two 128-row MMA groups)
+    DevBuf<Int4Pod> tiles2;
+    DevBuf<int> num_tiles2;
+    // output-stationary form for K = 55 tables: per output row the gather index of the 7
+    // "common" slots (self + 6 same-level faces), -1 = absent; the remaining (finer / coarser)
+    // entries form their own pair-major plan.
+    DevBuf<int32_t> cidx;         // [V_out][8]
+    std::unique_ptr<ConvPlan> rare;
+    int64_t E_common = 0;
 };
 
 void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, const int64_t* d_splits, int64_t V_out,
-                     int64_t E, int K, cudaStream_t s);
+                     int64_t E, int K, cudaStream_t s, bool with_output_stationary = true);
 
 // out must hold V_out*Cout floats.  imp_in (per input row, gathered through the
 // index) and/or imp_entry (per CSR entry) weight channels >= imp_col;
@@ -35,6 +46,13 @@ size_t packed_conv_filters_floats(int K, int Cin, int Cout);
 void pack_conv_filters(const float* W, int K, int Cin, int Cout, float* out, cudaStream_t s);
 void sparse_conv_tc_tiles(const ConvPlan& P, const float* x, const float* wp, int Cin, int Cout, const float* imp_in,
                           const float* imp_entry, int imp_col, float* out, cudaStream_t s);
+
+// output-stationary tensor-core path (common slots in TMEM, rare slots pair-major); see sparse_conv_os.cu
+void sparse_conv_tc_tune(int stages, int mt);
+void sparse_conv_os_enable(bool on);  // off by default, see DESIGN.md §4
+bool sparse_conv_os_supported(const ConvPlan& P, int Cin, int Cout);
+void sparse_conv_os(const ConvPlan& P, const float* x, const float* wp, int Cin, int Cout, const float* bias, int relu,
+                    float* out, cudaStream_t s);
 
 void row_importance(const float* imp, const int32_t* idx, const int64_t* splits, int64_t V, float* out,
                     cudaStream_t s);

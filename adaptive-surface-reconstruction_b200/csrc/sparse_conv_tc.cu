@@ -33,42 +33,19 @@
 namespace asrb {
 
 namespace {
+using umma::bulk_copy_g2s;
+using umma::kA_LBO;
+using umma::kA_SBO;
+using umma::kATileBytes;
+using umma::kB_LBO;
+using umma::kB_SBO;
+using umma::make_desc;
+using umma::mbar_arrive;
+using umma::mbar_expect_tx;
+using umma::red_add_v4;
 constexpr int TM = 128;
-constexpr int KC = 16;                           // input channels per pipeline stage (2 MMA k-steps)
+constexpr int KC = umma::kKC;                    // input channels per pipeline stage (2 MMA k-steps)
 constexpr int kMaxStages = 4;
-constexpr int kPrefetch = 4;                     // chunks of gathered rows held in registers
-constexpr uint32_t kA_LBO = 144;                 // padded: conflict-free staged stores
-constexpr uint32_t kA_SBO = (KC / 4) * kA_LBO;   // 576
-constexpr uint32_t kATileBytes = 16 * kA_SBO;    // 128 rows -> 9216 B
-constexpr uint32_t kB_LBO = 128;
-constexpr uint32_t kB_SBO = (KC / 4) * kB_LBO;   // 512
-constexpr int kProducerThreads = 128;
-constexpr int kThreadsTc = kProducerThreads + 32;
-
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
-    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(umma::smem_u32(mbar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(mbar)) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* mbar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         umma::smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(umma::smem_u32(mbar))
-                 : "memory");
-}
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 }  // namespace
 
 struct TcArgs {
@@ -83,33 +60,47 @@ struct TcArgs {
     const float* imp_entry;
     float* out;
     int Cin, Cout, n_pad, imp_col, stages;
+    int n_tile;  // output channels handled by one CTA (n_pad, or 128 with blockIdx.y selecting the half)
 };
 
-// Warp roles: warps 0-3 = producers (gather + hi/lo split) and, after the main
-// loop, the epilogue (warp w owns TMEM lanes 32w..32w+31); warp 4 = MMA issuer.
-__global__ void __launch_bounds__(kThreadsTc)
+// MT = number of 128-row MMA groups per CTA (tile = 128 * MT pairs).  MT = 2 halves the
+// L2 traffic of the filter chunks (one B stage feeds both groups) and the per-tile fixed cost;
+// it needs 2 * MT * n_pad TMEM columns, so it is used for n_pad <= 128.
+// Warp roles: warps 0 .. 4 MT - 1 = producers (gather + hi/lo split) and, after the main
+// loop, the epilogue (warp w: group w / 4, TMEM lanes 32 (w % 4) ..); last warp = MMA issuer.
+// PF = chunks of gathered rows a producer keeps in flight in registers (2 for the short
+// pipelines of Cin <= 64, which frees registers for 6 resident CTAs per SM; 4 otherwise).
+template <int MT, int PF>
+__global__ void __launch_bounds__(128 * MT + 32, MT == 2 ? 1 : (PF == 2 ? 5 : 4))
 sparse_conv_tc_kernel(TcArgs a) {
+    constexpr int kPrefetch = PF;
+    constexpr int kProducerThreads = 128 * MT;
+    constexpr int kMmaWarp = 4 * MT;
+    constexpr int TMC = TM * MT;
     extern __shared__ __align__(1024) uint8_t smem[];
-    // stage s: A_hi | A_lo | B_hi | B_lo
-    const uint32_t b_bytes = (uint32_t)a.n_pad * KC * 4;
-    const uint32_t stage_bytes = 2 * kATileBytes + 2 * b_bytes;
+    // stage s: MT x (A_hi | A_lo), then B_hi | B_lo
+    const int NT = a.n_tile;
+    const int col0 = blockIdx.y * NT;
+    const uint32_t b_bytes = (uint32_t)NT * KC * 4;
+    const uint32_t stage_bytes = MT * 2 * kATileBytes + 2 * b_bytes;
     __shared__ uint64_t mbar_full[kMaxStages];   // 128 producer arrivals + B bytes
     __shared__ uint64_t mbar_empty[kMaxStages];  // tcgen05.commit: the MMAs that read the stage are done
     __shared__ uint64_t mbar_acc;                // all MMAs of the tile are done
     __shared__ uint32_t tmem_slot;
-    __shared__ int s_in[TM];
-    __shared__ int s_out[TM];
-    __shared__ float s_imp[TM];
+    __shared__ int s_in[TMC];
+    __shared__ int s_out[TMC];
+    __shared__ float s_imp[TMC];
 
     if ((int)blockIdx.x >= *a.num_tiles) return;
     const int4 tile = a.tiles[blockIdx.x];
     const int slot = tile.x, start = tile.y, count = tile.z;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int S = a.stages;
-    // two accumulators: main at column 0, corrections at column n_pad
-    const uint32_t ncols = a.n_pad <= 16 ? 32 : a.n_pad <= 32 ? 64 : a.n_pad <= 64 ? 128 : a.n_pad <= 128 ? 256 : 512;
+    // per group g two accumulators: main at column 2 g n_pad, corrections at 2 g n_pad + n_pad
+    const uint32_t need = 2 * MT * NT;
+    const uint32_t ncols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
 
-    if (warp == 4) {
+    if (warp == kMmaWarp) {
         umma::tmem_alloc(&tmem_slot, ncols);
         if ((tid & 31) == 0) {
             for (int i = 0; i < S; ++i) {
@@ -120,7 +111,7 @@ sparse_conv_tc_kernel(TcArgs a) {
             umma::fence_barrier_init();
         }
     }
-    if (tid < TM) {
+    if (tid < TMC) {
         const bool ok = tid < count;
         const int pin = ok ? a.p_in[start + tid] : -1;
         s_in[tid] = pin;
@@ -138,14 +129,15 @@ sparse_conv_tc_kernel(TcArgs a) {
     const int chunks = (Cin + KC - 1) / KC;
     const float* wslot = a.wp + (size_t)slot * chunks * 2 * a.n_pad * KC;
 
-    if (warp < 4) {
+    if (warp < kMmaWarp) {
         // ------------------------------------------------------------ producers
-        const int kq = tid & 3;     // 16-byte column of the chunk
-        const int rsub = tid >> 2;  // 0..31: row within a pass (4 passes of 32 rows)
+        const int grp = tid >> 7;           // 128-row group of this thread
+        const int kq = tid & 3;             // 16-byte column of the chunk
+        const int rsub = (tid & 127) >> 2;  // 0..31: row within a pass (4 passes of 32 rows)
         const float* rowp[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int pin = s_in[rsub + 32 * j];
+            const int pin = s_in[grp * TM + rsub + 32 * j];
             rowp[j] = pin >= 0 ? a.x + (size_t)pin * Cin + kq * 4 : nullptr;
         }
         float4 v[kPrefetch][4];
@@ -165,13 +157,16 @@ sparse_conv_tc_kernel(TcArgs a) {
                 const int c = c0 + d;
                 if (c < chunks) {
                     const int st = c % S, use = c / S;
-                    uint8_t* sA_hi = smem + st * stage_bytes;
+                    uint8_t* sA_hi = smem + st * stage_bytes + grp * 2 * kATileBytes;
                     uint8_t* sA_lo = sA_hi + kATileBytes;
                     if (use > 0) umma::mbar_wait(&mbar_empty[st], (use - 1) & 1);
                     if (tid == 0) {
+                        // hi and lo halves of the chunk, rows [col0, col0 + NT) of each
+                        uint8_t* sB = smem + st * stage_bytes + MT * 2 * kATileBytes;
+                        const float* src = wslot + (size_t)c * 2 * a.n_pad * KC + (size_t)col0 * KC;
                         mbar_expect_tx(&mbar_full[st], 2 * b_bytes);
-                        bulk_copy_g2s(sA_lo + kATileBytes, wslot + (size_t)c * 2 * a.n_pad * KC, 2 * b_bytes,
-                                      &mbar_full[st]);
+                        bulk_copy_g2s(sB, src, b_bytes, &mbar_full[st]);
+                        bulk_copy_g2s(sB + b_bytes, src + (size_t)a.n_pad * KC, b_bytes, &mbar_full[st]);
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -199,17 +194,18 @@ sparse_conv_tc_kernel(TcArgs a) {
         // 128 contiguous bytes (full 32-byte sectors) instead of 32 rows x 16 bytes.
         float* T = reinterpret_cast<float*>(smem) + (size_t)warp * 32 * 36;  // [32 rows][36] per warp
         const int lane = tid & 31;
-        for (int n0 = 0; n0 < a.n_pad; n0 += 32) {
+        const uint32_t t_acc = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * 2 * NT;
+        for (int n0 = 0; n0 < NT; n0 += 32) {
             float acc[32], cor[32];
-            umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + n0, acc);
-            umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + a.n_pad + n0, cor);
+            umma::tmem_ld32(t_acc + n0, acc);
+            umma::tmem_ld32(t_acc + NT + n0, cor);
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
                 *reinterpret_cast<float4*>(T + lane * 36 + j) =
                         make_float4(acc[j] + cor[j], acc[j + 1] + cor[j + 1], acc[j + 2] + cor[j + 2], acc[j + 3] + cor[j + 3]);
             __syncwarp();
             const int cg = lane & 7;
-            const int n = n0 + cg * 4;
+            const int n = col0 + n0 + cg * 4;
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
                 const int rl = it * 4 + (lane >> 3);
@@ -228,21 +224,26 @@ sparse_conv_tc_kernel(TcArgs a) {
         }
     } else if ((tid & 31) == 0) {
         // ------------------------------------------------------------ MMA issuer
-        const uint32_t idesc = umma::make_idesc_tf32(128, a.n_pad);
+        const uint32_t idesc = umma::make_idesc_tf32(128, NT);
+        const int groups = (MT == 2 && count > TM) ? 2 : 1;  // a half-empty tile skips its second group
         for (int c = 0; c < chunks; ++c) {
             const int st = c % S, use = c / S;
             umma::mbar_wait(&mbar_full[st], use & 1);
             umma::tc_fence_after();
-            const uint32_t a_hi = umma::smem_u32(smem + st * stage_bytes), a_lo = a_hi + kATileBytes;
-            const uint32_t b_hi = a_lo + kATileBytes, b_lo = b_hi + b_bytes;
+            const uint32_t s_base = umma::smem_u32(smem + st * stage_bytes);
+            const uint32_t b_hi = s_base + MT * 2 * kATileBytes, b_lo = b_hi + b_bytes;
+            for (int g = 0; g < groups; ++g) {
+                const uint32_t a_hi = s_base + g * 2 * kATileBytes, a_lo = a_hi + kATileBytes;
+                const uint32_t t_main = tmem + g * 2 * NT, t_corr = t_main + NT;
 #pragma unroll
-            for (int ks = 0; ks < KC / 8; ++ks) {
-                const uint32_t oa = ks * 2 * kA_LBO, ob = ks * 2 * kB_LBO;
-                const uint64_t dah = make_desc(a_hi + oa, kA_LBO, kA_SBO), dal = make_desc(a_lo + oa, kA_LBO, kA_SBO);
-                const uint64_t dbh = make_desc(b_hi + ob, kB_LBO, kB_SBO), dbl = make_desc(b_lo + ob, kB_LBO, kB_SBO);
-                umma::mma_tf32(tmem, dah, dbh, idesc, c > 0 || ks > 0);
-                umma::mma_tf32(tmem + a.n_pad, dal, dbh, idesc, c > 0 || ks > 0);
-                umma::mma_tf32(tmem + a.n_pad, dah, dbl, idesc, true);
+                for (int ks = 0; ks < KC / 8; ++ks) {
+                    const uint32_t oa = ks * 2 * kA_LBO, ob = ks * 2 * kB_LBO;
+                    const uint64_t dah = make_desc(a_hi + oa, kA_LBO, kA_SBO), dal = make_desc(a_lo + oa, kA_LBO, kA_SBO);
+                    const uint64_t dbh = make_desc(b_hi + ob, kB_LBO, kB_SBO), dbl = make_desc(b_lo + ob, kB_LBO, kB_SBO);
+                    umma::mma_tf32(t_main, dah, dbh, idesc, c > 0 || ks > 0);
+                    umma::mma_tf32(t_corr, dal, dbh, idesc, c > 0 || ks > 0);
+                    umma::mma_tf32(t_corr, dah, dbl, idesc, true);
+                }
             }
             umma::mma_commit(&mbar_empty[st]);
         }
@@ -250,7 +251,7 @@ sparse_conv_tc_kernel(TcArgs a) {
     }
     umma::tc_fence_before();
     __syncthreads();
-    if (warp == 4) umma::tmem_dealloc(tmem, ncols);
+    if (warp == kMmaWarp) umma::tmem_dealloc(tmem, ncols);
 }
 
 // [K slots][Cin][Cout] fp32 -> packed hi/lo tiles, see TcArgs::wp
@@ -276,6 +277,14 @@ pack_conv_filters_kernel(const float* __restrict__ W, int K, int Cin, int Cout, 
     }
 }
 
+// tuning knobs (asr_set_option): pipeline depth for n_pad <= 128 and row groups per CTA
+static int g_tc_stages = 2;
+static int g_tc_mt = 1;
+void sparse_conv_tc_tune(int stages, int mt) {
+    if (stages > 0) g_tc_stages = std::min(stages, kMaxStages);
+    if (mt > 0) g_tc_mt = mt >= 2 ? 2 : 1;
+}
+
 size_t packed_conv_filters_floats(int K, int Cin, int Cout) {
     const int n_pad = ((Cout + 15) / 16) * 16;
     return (size_t)K * ((Cin + KC - 1) / KC) * 2 * n_pad * KC;
@@ -299,8 +308,10 @@ void sparse_conv_tc_tiles(const ConvPlan& P, const float* x, const float* wp, in
     a.p_in = P.p_in.get();
     a.p_out = P.p_out.get();
     a.perm = P.perm.get();
-    a.tiles = (const int4*)P.tiles.get();
-    a.num_tiles = P.num_tiles.get();
+    a.n_tile = std::min(n_pad, 128);
+    const int MT = g_tc_mt == 2 ? 2 : 1;
+    a.tiles = (const int4*)(MT == 2 ? P.tiles2.get() : P.tiles.get());
+    a.num_tiles = MT == 2 ? P.num_tiles2.get() : P.num_tiles.get();
     a.imp_in = imp_in;
     a.imp_entry = imp_entry;
     a.out = out;
@@ -309,14 +320,20 @@ void sparse_conv_tc_tiles(const ConvPlan& P, const float* x, const float* wp, in
     a.n_pad = n_pad;
     a.imp_col = (imp_in || imp_entry) ? imp_col : Cout;
     const int chunks = (Cin + KC - 1) / KC;
-    const size_t stage = 2 * (size_t)kATileBytes + 2 * (size_t)n_pad * KC * 4;
-    a.stages = std::max(1, std::min({n_pad > 128 ? kMaxStages : 3, chunks, (int)((200 * 1024) / stage)}));
-    const size_t smem = a.stages * stage;
-    ASRB_CUDA(cudaFuncSetAttribute(sparse_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t stage = MT * 2 * (size_t)kATileBytes + 2 * (size_t)a.n_tile * KC * 4;
+    a.stages = std::max(1, std::min({g_tc_stages, chunks, (int)((200 * 1024) / stage)}));
+    const size_t smem = std::max<size_t>(a.stages * stage, (size_t)4 * MT * 32 * 36 * sizeof(float));
     char label[96];
     snprintf(label, sizeof(label), "sparse_conv_tile/tc K%d %dx%d E%lld", P.K, Cin, Cout, (long long)P.E);
     ProfileScope prof(label, s, 2.0 * (double)P.E * Cin * Cout);
-    sparse_conv_tc_kernel<<<(unsigned)P.max_tiles, kThreadsTc, smem, s>>>(a);
+    const unsigned ny = (unsigned)(n_pad / a.n_tile);
+    auto launch = [&](auto kernel, int max_tiles, int threads) {
+        ASRB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<dim3((unsigned)max_tiles, ny), threads, smem, s>>>(a);
+    };
+    if (MT == 2) launch(sparse_conv_tc_kernel<2, 4>, P.max_tiles2, 288);
+    else if (Cin <= 64) launch(sparse_conv_tc_kernel<1, 2>, P.max_tiles, 160);
+    else launch(sparse_conv_tc_kernel<1, 4>, P.max_tiles, 160);
     ASRB_CHECK_LAUNCH();
 }
 

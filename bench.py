@@ -184,6 +184,7 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     _lib.lib()
     ops.SPARSE_CONV_BACKEND = args.backend
+    _lib.set_option("sparse_conv_output_stationary", args.conv_os)
     peaks = load_peaks()
 
     # N > 1: ONE cloud, the path sharded by output-voxel ranges across the ranks with an all-gather
@@ -345,6 +346,7 @@ def main():
     ap.add_argument("--cpu-points", type=int, default=200_000, help="bounded sample for the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--backend", default="tensor", choices=["tensor", "fp32"], help="sparse-conv contraction")
+    ap.add_argument("--conv-os", type=int, default=0, help="1: output-stationary kernel for the plain K=55 convs")
     ap.add_argument("--profile-run", action="store_true",
                     help="for runs under ncu: no minimum warm-up, no e2e leg; the printed numbers are NOT bench values")
     args = ap.parse_args()

@@ -39,6 +39,10 @@ const char* asr_last_error(void);
 /* number of kernels this library has launched since load (bench.py gpu_launches) */
 int64_t asr_kernel_launches(void);
 
+/* Library options.  "sparse_conv_output_stationary" (default 0): run the within-grid convolutions
+ * that carry no importance through the output-stationary tensor-core kernel (sparse_conv_os.cu). */
+int asr_set_option(const char* name, int value);
+
 /* Per-kernel device timing (CUDA events on the launching stream) for bench.py's
  * roofline figures: enable, run, then read (name, total ms, launches, algorithmic
  * flops) per instrumented kernel.  Reading synchronises the recorded events. */
