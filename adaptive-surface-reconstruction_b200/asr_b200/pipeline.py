@@ -99,6 +99,21 @@ def reconstruct_vertices(model, points, normals, radii, bb_min=None, bb_max=None
             "input_dict": d, "octree": tree}
 
 
+_PINNED = {}
+
+
+def _to_host(t, key):
+    """D2H through a cached pinned staging buffer (grown on demand)."""
+    n = t.numel()
+    buf = _PINNED.get(key)
+    if buf is None or buf.numel() < n or buf.dtype != t.dtype:
+        buf = torch.empty(max(n, 1) * 5 // 4, dtype=t.dtype, pin_memory=True)
+        _PINNED[key] = buf
+    view = buf[:n].view(t.shape)
+    view.copy_(t, non_blocking=True)
+    return view
+
+
 def reconstruct_vertices_host(model, points, normals, radii, bb_min=None, bb_max=None, **kw):
     """Same path with HOST (numpy) buffers in and out: H2D of the cloud, the
     device path, D2H of the vertices and SDF values.  This is the call the
@@ -110,4 +125,6 @@ def reconstruct_vertices_host(model, points, normals, radii, bb_min=None, bb_max
     if bb_min is None:
         bb_min, bb_max = points.min(0), points.max(0)
     out = reconstruct_vertices(model, p, n, r, bb_min, bb_max, **kw)
-    return {"vertices": out["vertices"].cpu().numpy(), "values": out["values"].cpu().numpy()}
+    v, s = _to_host(out["vertices"], "vertices"), _to_host(out["values"], "values")
+    torch.cuda.current_stream().synchronize()
+    return {"vertices": v.numpy().copy(), "values": s.numpy().copy()}

@@ -208,11 +208,14 @@ void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, c
     tile_list_kernel<<<1, 256, 0, s>>>(keys.get(), E, K, std::max(num_blocks, 1), TM, g_begin.get(), g_tile0.get(),
                                        (int4*)P.tiles.get(), P.num_tiles.get());
     ASRB_CHECK_LAUNCH();
-    tile_list_kernel<<<1, 256, 0, s>>>(keys.get(), E, K, std::max(num_blocks, 1), 2 * TM, g_begin.get(), g_tile0.get(),
-                                       (int4*)P.tiles2.get(), P.num_tiles2.get());
-    ASRB_CHECK_LAUNCH();
+    if (sparse_conv_tc_row_groups() == 2) {
+        tile_list_kernel<<<1, 256, 0, s>>>(keys.get(), E, K, std::max(num_blocks, 1), 2 * TM, g_begin.get(),
+                                           g_tile0.get(), (int4*)P.tiles2.get(), P.num_tiles2.get());
+        ASRB_CHECK_LAUNCH();
+        P.has_tiles2 = true;
+    }
 
-    if (with_output_stationary && K == 55 && V_out > 0) {
+    if (with_output_stationary && sparse_conv_os_enabled() && K == 55 && V_out > 0) {
         P.cidx.alloc((size_t)V_out * 8, s);
         DevBuf<int32_t> rare_count((size_t)V_out, s);
         DevBuf<int64_t> rsplits((size_t)V_out + 1, s);

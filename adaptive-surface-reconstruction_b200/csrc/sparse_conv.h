@@ -18,6 +18,7 @@ struct ConvPlan {
     DevBuf<uint32_t> perm;        // [E] original CSR position of each sorted pair
     DevBuf<Int4Pod> tiles;        // (slot, first pair, count, -)
     DevBuf<int> num_tiles;        // device scalar
+    bool has_tiles2 = false;      // built only when the 2-row-group option is on at plan creation
     int max_tiles2 = 0;           // same for 256-pair tiles (tensor-core kernel, two 128-row MMA groups)
     DevBuf<Int4Pod> tiles2;
     DevBuf<int> num_tiles2;
@@ -49,7 +50,9 @@ void sparse_conv_tc_tiles(const ConvPlan& P, const float* x, const float* wp, in
 
 // output-stationary tensor-core path (common slots in TMEM, rare slots pair-major); see sparse_conv_os.cu
 void sparse_conv_tc_tune(int stages, int mt);
-void sparse_conv_os_enable(bool on);  // off by default, see DESIGN.md §4
+int sparse_conv_tc_row_groups();
+void sparse_conv_os_enable(bool on);
+bool sparse_conv_os_enabled();  // off by default, see DESIGN.md §4
 bool sparse_conv_os_supported(const ConvPlan& P, int Cin, int Cout);
 void sparse_conv_os(const ConvPlan& P, const float* x, const float* wp, int Cin, int Cout, const float* bias, int relu,
                     float* out, cudaStream_t s);

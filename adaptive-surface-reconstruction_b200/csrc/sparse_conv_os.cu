@@ -231,6 +231,7 @@ sparse_conv_os_kernel(OsArgs a) {
 
 static bool g_os_enabled = false;
 void sparse_conv_os_enable(bool on) { g_os_enabled = on; }
+bool sparse_conv_os_enabled() { return g_os_enabled; }
 
 bool sparse_conv_os_supported(const ConvPlan& P, int Cin, int Cout) {
     return g_os_enabled && P.K == 55 && P.rare && P.cidx.size() && Cin <= 128 && Cout <= 128 && Cin % 4 == 0 && Cout % 4 == 0;

@@ -285,6 +285,8 @@ void sparse_conv_tc_tune(int stages, int mt) {
     if (mt > 0) g_tc_mt = mt >= 2 ? 2 : 1;
 }
 
+int sparse_conv_tc_row_groups() { return g_tc_mt; }
+
 size_t packed_conv_filters_floats(int K, int Cin, int Cout) {
     const int n_pad = ((Cout + 15) / 16) * 16;
     return (size_t)K * ((Cin + KC - 1) / KC) * 2 * n_pad * KC;
@@ -309,7 +311,7 @@ void sparse_conv_tc_tiles(const ConvPlan& P, const float* x, const float* wp, in
     a.p_out = P.p_out.get();
     a.perm = P.perm.get();
     a.n_tile = std::min(n_pad, 128);
-    const int MT = g_tc_mt == 2 ? 2 : 1;
+    const int MT = (g_tc_mt == 2 && P.has_tiles2) ? 2 : 1;
     a.tiles = (const int4*)(MT == 2 ? P.tiles2.get() : P.tiles.get());
     a.num_tiles = MT == 2 ? P.num_tiles2.get() : P.num_tiles.get();
     a.imp_in = imp_in;

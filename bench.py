@@ -205,8 +205,9 @@ def run_gpu(args):
         n = host["normals"].cuda(non_blocking=True)
         r = host["radii"].cuda(non_blocking=True)
         out = pipeline.reconstruct_vertices(net, p, n, r, bb[0], bb[1])
-        v = out["vertices"].cpu()
-        s = out["values"].cpu()
+        v = pipeline._to_host(out["vertices"], "bench_vertices")
+        s = pipeline._to_host(out["values"], "bench_values")
+        torch.cuda.current_stream().synchronize()  # the step's results are on the host
         return out, v, s
 
     def barrier():
