@@ -89,6 +89,11 @@ int asr_set_option(const char* name, int value) {
     return guarded([&] {
         ASRB_REQUIRE(name != nullptr, "option name is null");
         if (std::string(name) == "sparse_conv_output_stationary") sparse_conv_os_enable(value != 0);
+        else if (std::string(name) == "sparse_conv_persistent") sparse_conv_pm_enable(value != 0);
+        else if (std::string(name) == "pm_debug") {
+            sparse_conv_pm_debug(value);
+            sparse_conv_os_debug(value);
+        }
         else if (std::string(name) == "tc_stages") sparse_conv_tc_tune(value, 0);
         else if (std::string(name) == "tc_row_groups") sparse_conv_tc_tune(0, value);
         else throw Error(kInvalidArgument, std::string("unknown option: ") + name);

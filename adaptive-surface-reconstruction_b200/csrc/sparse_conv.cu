@@ -116,57 +116,12 @@ tile_list_kernel(const uint32_t* __restrict__ sorted_key, long long E, int K, in
     }
     __syncthreads();
     int t = s_part[threadIdx.x];
+    if (threadIdx.x == 0 && g_tile0) g_tile0[G] = *num_tiles;
     for (int g = g0; g < g1; ++g) {
         const long long b = g_begin[g], e = g_begin[g + 1];
+        if (g_tile0) g_tile0[g] = t;
         for (long long start = b; start < e; start += tile_rows)
             tiles[t++] = make_int4(g % K, (int)start, (int)min((long long)tile_rows, e - start), 0);
-    }
-}
-
-constexpr int kCommonSlots = 7;  // self + 6 same-level face neighbours
-
-__global__ void __launch_bounds__(256)
-common_index_kernel(const int32_t* __restrict__ idx, const uint8_t* __restrict__ slot, const int64_t* __restrict__ splits,
-                    long long V, int32_t* __restrict__ cidx, int32_t* __restrict__ rare_count) {
-    long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (v >= V) return;
-    int c[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
-    int rare = 0;
-    const int64_t e = splits[v + 1];
-    for (int64_t j = splits[v]; j < e; ++j) {
-        const int k = slot[j];
-        if (k < kCommonSlots) {
-            if (c[k] >= 0) ++rare;  // a duplicate slot within a row (never produced by the grid code): keep it pair-major
-            else c[k] = idx[j];
-        } else {
-            ++rare;
-        }
-    }
-    reinterpret_cast<int4*>(cidx)[2 * v] = make_int4(c[0], c[1], c[2], c[3]);
-    reinterpret_cast<int4*>(cidx)[2 * v + 1] = make_int4(c[4], c[5], c[6], c[7]);
-    rare_count[v] = rare;
-}
-
-__global__ void __launch_bounds__(256)
-rare_fill_kernel(const int32_t* __restrict__ idx, const uint8_t* __restrict__ slot, const int64_t* __restrict__ splits,
-                 long long V, const int64_t* __restrict__ rsplits, int32_t* __restrict__ ridx, uint8_t* __restrict__ rslot) {
-    long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (v >= V) return;
-    unsigned seen = 0;
-    int64_t o = rsplits[v];
-    const int64_t e = splits[v + 1];
-    for (int64_t j = splits[v]; j < e; ++j) {
-        const int k = slot[j];
-        bool rare = k >= kCommonSlots;
-        if (!rare) {
-            if (seen & (1u << k)) rare = true;
-            seen |= 1u << k;
-        }
-        if (rare) {
-            ridx[o] = idx[j];
-            rslot[o] = (uint8_t)k;
-            ++o;
-        }
     }
 }
 
@@ -192,8 +147,11 @@ void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, c
     ProfileScope prof("conv_plan_build", s);
     DevBuf<uint32_t> rows((size_t)E, s);
     DevBuf<uint32_t> keys((size_t)E, s);
-    DevBuf<long long> g_begin((size_t)G + 1, s);
-    DevBuf<int> g_tile0((size_t)G + 1, s);
+    P.G = G;
+    P.g_begin.alloc((size_t)G + 1, s);
+    P.g_tile0.alloc((size_t)G + 1, s);
+    DevBuf<long long>& g_begin = P.g_begin;
+    DevBuf<int>& g_tile0 = P.g_tile0;
     if (E) {
         entry_rows_kernel<<<grid_for((size_t)V_out * 8, 256), 256, 0, s>>>(d_splits, V_out, d_slot, rows.get(),
                                                                           keys.get(), P.perm.get());
@@ -209,32 +167,15 @@ void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, c
                                        (int4*)P.tiles.get(), P.num_tiles.get());
     ASRB_CHECK_LAUNCH();
     if (sparse_conv_tc_row_groups() == 2) {
-        tile_list_kernel<<<1, 256, 0, s>>>(keys.get(), E, K, std::max(num_blocks, 1), 2 * TM, g_begin.get(),
-                                           g_tile0.get(), (int4*)P.tiles2.get(), P.num_tiles2.get());
+        DevBuf<long long> g_begin2((size_t)G + 1, s);
+        tile_list_kernel<<<1, 256, 0, s>>>(keys.get(), E, K, std::max(num_blocks, 1), 2 * TM, g_begin2.get(),
+                                           nullptr, (int4*)P.tiles2.get(), P.num_tiles2.get());
         ASRB_CHECK_LAUNCH();
         P.has_tiles2 = true;
     }
 
-    if (with_output_stationary && sparse_conv_os_enabled() && K == 55 && V_out > 0) {
-        P.cidx.alloc((size_t)V_out * 8, s);
-        DevBuf<int32_t> rare_count((size_t)V_out, s);
-        DevBuf<int64_t> rsplits((size_t)V_out + 1, s);
-        common_index_kernel<<<grid_for(V_out, 256), 256, 0, s>>>(d_idx, d_slot, d_splits, V_out, P.cidx.get(),
-                                                                 rare_count.get());
-        ASRB_CHECK_LAUNCH();
-        exclusive_sum_i32_to_i64(rare_count.get(), rsplits.get(), (size_t)V_out, s);
-        const int64_t E_rare = d2h_scalar(rsplits.get() + V_out, s);
-        P.E_common = E - E_rare;
-        DevBuf<int32_t> ridx((size_t)E_rare, s);
-        DevBuf<uint8_t> rslot((size_t)E_rare, s);
-        if (E_rare) {
-            rare_fill_kernel<<<grid_for(V_out, 256), 256, 0, s>>>(d_idx, d_slot, d_splits, V_out, rsplits.get(),
-                                                                  ridx.get(), rslot.get());
-            ASRB_CHECK_LAUNCH();
-        }
-        P.rare = std::make_unique<ConvPlan>();
-        conv_plan_build(*P.rare, ridx.get(), rslot.get(), rsplits.get(), V_out, E_rare, K, s, false);
-    }
+    if (with_output_stationary && sparse_conv_os_enabled() && K == 55 && V_out > 0)
+        os_plan_build(P, d_idx, d_slot, d_splits, V_out, K, s);
 }
 
 // ------------------------------------------------------------------ tile kernel
@@ -504,7 +445,9 @@ void sparse_conv_forward(const ConvPlan& P, const float* x, const float* w, cons
         ProfileScope prof("sparse_conv_zero", s);
         ASRB_CUDA(cudaMemsetAsync(out, 0, (size_t)P.V_out * Cout * sizeof(float), s));
     }
-    if (P.E > 0 && wp) {
+    if (P.E > 0 && wp && sparse_conv_pm_supported(P, Cin, Cout)) {
+        sparse_conv_pm_tiles(P, x, wp, Cin, Cout, imp_in, imp_entry, imp_col, out, s);
+    } else if (P.E > 0 && wp) {
         sparse_conv_tc_tiles(P, x, wp, Cin, Cout, imp_in, imp_entry, imp_col, out, s);
     } else if (P.E > 0) {
         TileArgs a;

@@ -18,20 +18,28 @@ struct ConvPlan {
     DevBuf<uint32_t> perm;        // [E] original CSR position of each sorted pair
     DevBuf<Int4Pod> tiles;        // (slot, first pair, count, -)
     DevBuf<int> num_tiles;        // device scalar
+    // (row block, slot) groups, g = block * K + slot: first pair and number of 128-pair tiles
+    // before each group ([G + 1] each); the persistent kernel walks these instead of `tiles`
+    int G = 0;
+    DevBuf<long long> g_begin;
+    DevBuf<int> g_tile0;
     bool has_tiles2 = false;      // built only when the 2-row-group option is on at plan creation
     int max_tiles2 = 0;           // same for 256-pair tiles (tensor-core kernel, two 128-row MMA groups)
     DevBuf<Int4Pod> tiles2;
     DevBuf<int> num_tiles2;
-    // output-stationary form for K = 55 tables: per output row the gather index of the 7
-    // "common" slots (self + 6 same-level faces), -1 = absent; the remaining (finer / coarser)
-    // entries form their own pair-major plan.
-    DevBuf<int32_t> cidx;         // [V_out][8]
-    std::unique_ptr<ConvPlan> rare;
-    int64_t E_common = 0;
+    // output-stationary form (sparse_conv_os.cu): per super-tile of 256 output rows the slots
+    // that occur ("steps") and per step the gather index of every row (-1 = absent)
+    bool os_ok = false;
+    int64_t os_steps = 0, os_tiles = 0;
+    DevBuf<int64_t> os_off;   // [os_tiles + 1]
+    DevBuf<int32_t> os_meta;  // [os_steps] slot | row-tile flags << 8
+    DevBuf<int32_t> os_idx;   // [os_steps][256]
 };
 
 void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, const int64_t* d_splits, int64_t V_out,
                      int64_t E, int K, cudaStream_t s, bool with_output_stationary = true);
+void os_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, const int64_t* d_splits, int64_t V_out,
+                   int K, cudaStream_t s);
 
 // out must hold V_out*Cout floats.  imp_in (per input row, gathered through the
 // index) and/or imp_entry (per CSR entry) weight channels >= imp_col;
@@ -48,11 +56,20 @@ void pack_conv_filters(const float* W, int K, int Cin, int Cout, float* out, cud
 void sparse_conv_tc_tiles(const ConvPlan& P, const float* x, const float* wp, int Cin, int Cout, const float* imp_in,
                           const float* imp_entry, int imp_col, float* out, cudaStream_t s);
 
-// output-stationary tensor-core path (common slots in TMEM, rare slots pair-major); see sparse_conv_os.cu
+// persistent pair-major tensor-core kernel (sparse_conv_pm.cu): filter part resident in shared
+// memory, TMEM double buffering, bulk-reduction epilogue
+bool sparse_conv_pm_supported(const ConvPlan& P, int Cin, int Cout);
+void sparse_conv_pm_enable(bool on);
+void sparse_conv_pm_debug(int on);
+void sparse_conv_pm_tiles(const ConvPlan& P, const float* x, const float* wp, int Cin, int Cout, const float* imp_in,
+                          const float* imp_entry, int imp_col, float* out, cudaStream_t s);
+
+// output-stationary persistent tensor-core path; see sparse_conv_os.cu
 void sparse_conv_tc_tune(int stages, int mt);
 int sparse_conv_tc_row_groups();
 void sparse_conv_os_enable(bool on);
-bool sparse_conv_os_enabled();  // off by default, see DESIGN.md §4
+void sparse_conv_os_debug(int on);
+bool sparse_conv_os_enabled();
 bool sparse_conv_os_supported(const ConvPlan& P, int Cin, int Cout);
 void sparse_conv_os(const ConvPlan& P, const float* x, const float* wp, int Cin, int Cout, const float* bias, int relu,
                     float* out, cudaStream_t s);

@@ -189,39 +189,39 @@ sparse_conv_tc_kernel(TcArgs a) {
         // ------------------------------------------------------------ epilogue
         umma::mbar_wait(&mbar_acc, 0);
         umma::tc_fence_after();
-        // TMEM -> registers (thread = row) -> per-warp transpose through shared memory (the
-        // pipeline stages are idle now) so that each RED instruction of a warp covers 4 rows x
-        // 128 contiguous bytes (full 32-byte sectors) instead of 32 rows x 16 bytes.
-        float* T = reinterpret_cast<float*>(smem) + (size_t)warp * 32 * 36;  // [32 rows][36] per warp
+        // TMEM -> registers (thread = pair = TMEM lane) -> the pair's output row segment staged
+        // in shared memory (the pipeline stages are idle now; row stride NT * 4 + 16 bytes keeps
+        // the 16-byte stores conflict free) -> ONE bulk reduction (cp.reduce.async.bulk .add.f32,
+        // TMA engine) per pair adds the segment to its output row.  Compared with
+        // red.global.add.v4 from registers this takes the scatter off the LSU pipe, which ncu
+        // showed to be the limiter of this kernel (l1tex data-pipe wavefronts ~75 %).
         const int lane = tid & 31;
+        const int prow = warp * 32 + lane;            // pair index inside the tile
+        const uint32_t t_stride = (uint32_t)NT + 4;   // floats
+        float* T = reinterpret_cast<float*>(smem) + (size_t)prow * t_stride;
         const uint32_t t_acc = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * 2 * NT;
-        for (int n0 = 0; n0 < NT; n0 += 32) {
-            float acc[32], cor[32];
-            umma::tmem_ld32(t_acc + n0, acc);
-            umma::tmem_ld32(t_acc + NT + n0, cor);
+        const float imp = s_imp[prow];
+        for (int n0 = 0; n0 < NT; n0 += 16) {
+            float acc[16], cor[16];
+            umma::tmem_ld16(t_acc + n0, acc);
+            umma::tmem_ld16(t_acc + NT + n0, cor);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(T + lane * 36 + j) =
-                        make_float4(acc[j] + cor[j], acc[j + 1] + cor[j + 1], acc[j + 2] + cor[j + 2], acc[j + 3] + cor[j + 3]);
-            __syncwarp();
-            const int cg = lane & 7;
-            const int n = col0 + n0 + cg * 4;
+            for (int j = 0; j < 16; j += 4) {
+                float e[4];
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int rl = it * 4 + (lane >> 3);
-                const int o = s_out[warp * 32 + rl];
-                if (o >= 0 && n < a.Cout) {
-                    const float imp = s_imp[warp * 32 + rl];
-                    const float4 t = *reinterpret_cast<const float4*>(T + rl * 36 + cg * 4);
-                    float e[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (n + q >= a.imp_col) e[q] *= imp;
-                    red_add_v4(a.out + (size_t)o * a.Cout + n, e[0], e[1], e[2], e[3]);
+                for (int q = 0; q < 4; ++q) {
+                    e[q] = acc[j + q] + cor[j + q];
+                    if (col0 + n0 + j + q >= a.imp_col) e[q] *= imp;
                 }
+                *reinterpret_cast<float4*>(T + n0 + j) = make_float4(e[0], e[1], e[2], e[3]);
             }
-            __syncwarp();
         }
+        umma::fence_proxy_async();  // generic-proxy writes of this thread -> visible to the bulk (async proxy) read
+        const int o = s_out[prow];
+        const int ncol = min(NT, a.Cout - col0);
+        if (o >= 0 && ncol > 0) umma::bulk_reduce_add_f32(a.out + (size_t)o * a.Cout + col0, T, (uint32_t)ncol * 4);
+        umma::bulk_commit();
+        umma::bulk_wait_read();  // the staging rows live in this CTA's shared memory
     } else if ((tid & 31) == 0) {
         // ------------------------------------------------------------ MMA issuer
         const uint32_t idesc = umma::make_idesc_tf32(128, NT);
@@ -324,7 +324,7 @@ void sparse_conv_tc_tiles(const ConvPlan& P, const float* x, const float* wp, in
     const int chunks = (Cin + KC - 1) / KC;
     const size_t stage = MT * 2 * (size_t)kATileBytes + 2 * (size_t)a.n_tile * KC * 4;
     a.stages = std::max(1, std::min({g_tc_stages, chunks, (int)((200 * 1024) / stage)}));
-    const size_t smem = std::max<size_t>(a.stages * stage, (size_t)4 * MT * 32 * 36 * sizeof(float));
+    const size_t smem = std::max<size_t>(a.stages * stage, (size_t)128 * MT * (a.n_tile + 4) * sizeof(float));
     char label[96];
     snprintf(label, sizeof(label), "sparse_conv_tile/tc K%d %dx%d E%lld", P.K, Cin, Cout, (long long)P.E);
     ProfileScope prof(label, s, 2.0 * (double)P.E * Cin * Cout);

@@ -133,6 +133,79 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(mbar))
                  : "memory");
 }
+// 1-D bulk reduction shared -> global (TMA engine): global[i] += smem[i] for `bytes` / 4 floats,
+// element-wise atomic at L2; bytes % 16 == 0, both addresses 16-byte aligned.  Tracked by the
+// thread's bulk async-group (bulk_commit / bulk_wait_read).
+__device__ __forceinline__ void bulk_reduce_add_f32(float* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gmem_dst),
+                 "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+// 1-D bulk store shared -> global (TMA engine), same group tracking as the reduction
+__device__ __forceinline__ void bulk_store(float* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk groups of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// all committed bulk groups of this thread are complete (reads and global writes)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// arrive (count 1) and add `bytes` to the expected transaction count of the current phase
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+
+// split form of tmem_ld32: issue any number of loads, then bind the destination registers to
+// the wait so that no use can be scheduled before it
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr)
+            : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+// 16-byte async copy global -> shared (LDGSTS), zero-filled beyond src_bytes; L2 only
+__device__ __forceinline__ void cp_async16_cg(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one arrival (counted in its init count) when all cp.async issued so far
+// by this thread have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* mbar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
+}
+
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr)
+            : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+}
+
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -140,10 +213,17 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 // Operand-tile geometry shared by the sparse-conv tensor kernels: 16 input channels per
 // pipeline stage; A tiles (gathered rows) use a padded core-matrix stride so the staged
 // 16-byte stores of a warp spread evenly over the banks; B tiles are packed contiguously.
+// A staging pattern: lane = (row of a pair {2m, 2m+1}, 16-byte column kq): a quarter-warp
+// (one shared-memory phase of a 16-byte store) covers 2 rows x kq 0..3, i.e. byte offsets
+// kq * LBO + {0, 16} (+ 32 m).  The 8-row groups of one kq are packed densely (SBO = 128) and
+// the kq planes are 16 * 128 + 32 bytes apart: the four kq pieces land 8 banks apart (banks
+// 0, 8, 16, 24) and the second row in the 4-bank gap -> all 32 banks exactly once.
+// (The earlier LBO = 144 / SBO = 576 layout was 2-way conflicted: half of the store
+// wavefronts were replays and the LSU data pipe was the kernel's limiter, ncu r1.)
 constexpr int kKC = 16;
-constexpr uint32_t kA_LBO = 144;
-constexpr uint32_t kA_SBO = (kKC / 4) * kA_LBO;  // 576
-constexpr uint32_t kATileBytes = 16 * kA_SBO;    // 128 rows -> 9216 B
+constexpr uint32_t kA_SBO = 128;
+constexpr uint32_t kA_LBO = 16 * kA_SBO + 32;        // 2080
+constexpr uint32_t kATileBytes = (kKC / 4) * kA_LBO;  // 128 rows x 16 channels -> 8320 B
 constexpr uint32_t kB_LBO = 128;
 constexpr uint32_t kB_SBO = (kKC / 4) * kB_LBO;  // 512
 

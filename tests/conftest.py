@@ -33,3 +33,15 @@ def geom_checkers():
     if reflib.available():
         out.append(("reference", reflib.RefOctree))
     return out
+
+
+@pytest.fixture(autouse=True)
+def _reset_kernel_options(request):
+    """GPU tests may switch the optional sparse-conv kernels on; restore the defaults."""
+    yield
+    if "gpu" in request.keywords:
+        import torch
+        if torch.cuda.is_available():
+            from asr_b200 import _lib
+            for name in ("sparse_conv_output_stationary", "sparse_conv_persistent"):
+                _lib.set_option(name, 0)

@@ -99,12 +99,15 @@ def ref_with(imp, W, g, c, feats, idx, rs):
 
 @pytest.mark.parametrize("cin,cout", [(32, 64), (64, 128), (128, 32), (36, 56), (8, 8), (256, 256)])
 @pytest.mark.parametrize("level", [0, 1])
-@pytest.mark.parametrize("backend", ["tensor", "tensor_os", "fp32"])
+@pytest.mark.parametrize("backend", ["tensor", "tensor_os", "tensor_pm", "fp32"])
 def test_sparse_conv_within_grid(cin, cout, level, backend, monkeypatch):
+    """tensor = per-tile tcgen05 kernel (default); tensor_os / tensor_pm = the optional
+    output-stationary / persistent pair-major tcgen05 kernels; fp32 = FMA tile kernel."""
     from asr_b200 import _lib, ops
     from oracle import ops_cpu
     _lib.set_option("sparse_conv_output_stationary", backend == "tensor_os")
-    monkeypatch.setattr(ops, "SPARSE_CONV_BACKEND", "tensor" if backend == "tensor_os" else backend)
+    _lib.set_option("sparse_conv_persistent", backend == "tensor_pm")
+    monkeypatch.setattr(ops, "SPARSE_CONV_BACKEND", "tensor" if backend.startswith("tensor") else backend)
     c, t, grids = _scene(n=12000 if cin * cout > 20000 else 30000)
     g = grids[level]
     V = g["neighbors_row_splits"].shape[0] - 1
