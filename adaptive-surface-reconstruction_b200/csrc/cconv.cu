@@ -84,9 +84,15 @@ cconv_kernel(const float* __restrict__ filters,  // [S,S,S,Cin,Cout]  (z,y,x ord
 // importance loaded with 32-way memory parallelism, kernel coordinates computed
 // once per neighbour); phase B: the batch is replayed through warp shuffles with
 // lane = tap x channel, one conflict-free shared-memory update per neighbour.
+// The contraction with the filter bank runs for kCcGroup voxels of the warp at once
+// (lane = output channel): every filter value read from shared memory feeds kCcGroup
+// FMAs instead of one, which took the shared-memory pipe off the critical path.
 // Voxels without neighbours skip the contraction (output = act(bias)).
+constexpr int kCcGroup = 4;
+constexpr int kCc4Warps = 16;  // 32 KB filter bank + 16 x 4 KB cell tensors = 96 KB -> 2 blocks / SM, 32 warps
+
 template <int S>
-__global__ void __launch_bounds__(kCcWarps * 32)
+__global__ void __launch_bounds__(kCc4Warps * 32)
 cconv4_kernel(const float* __restrict__ filters, const float* __restrict__ out_pos,
               const float* __restrict__ extents, int extents_stride, const float* __restrict__ offset,
               const float* __restrict__ inp_pos, const float4* __restrict__ inp_feat,
@@ -96,91 +102,125 @@ cconv4_kernel(const float* __restrict__ filters, const float* __restrict__ out_p
     constexpr int CELLS = S * S * S, K = CELLS * 4;
     extern __shared__ float smem[];
     float* Ws = smem;                                   // [K][Cout]
-    float* Bs = smem + (size_t)K * Cout;                // [warps][K]
+    float* Bs = smem + (size_t)K * Cout;                // [warps][kCcGroup][K]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) Ws[i] = filters[i];
     __syncthreads();
-    float* B = Bs + warp * K;
+    float* Bw = Bs + (size_t)warp * kCcGroup * K;
     const float ox = offset ? offset[0] : 0.f, oy = offset ? offset[1] : 0.f, oz = offset ? offset[2] : 0.f;
     const float sm1 = (float)(S - 1);
     const int tap = lane >> 2, ch = lane & 3;
     const int tx = tap & 1, ty = (tap >> 1) & 1, tz = tap >> 2;
-    const long long nwarps = (long long)gridDim.x * kCcWarps;
-    for (long long v = blockIdx.x * (long long)kCcWarps + warp; v < V; v += nwarps) {
-        const int64_t b = splits[v], e = splits[v + 1];
-        float norm = 0.f;
-        if (e > b) {
-            for (int j = lane; j < K; j += 32) B[j] = 0.f;
-            __syncwarp();
-            const float cx = out_pos[3 * v], cy = out_pos[3 * v + 1], cz = out_pos[3 * v + 2];
-            const float scale = 2.0f / extents[v * extents_stride];
-            for (int64_t n0 = b; n0 < e; n0 += 32) {
-                const int cnt = (int)min((int64_t)32, e - n0);
-                // ---- phase A: lane = neighbour
-                float x = 0.f, y = 0.f, z = 0.f, imp = 0.f, nimp_l = 0.f;
-                float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (lane < cnt) {
-                    const int p = nidx[n0 + lane];
-                    nimp_l = nimp ? nimp[n0 + lane] : 1.0f;
-                    imp = inp_importance ? nimp_l * inp_importance[p] : nimp_l;
-                    f = __ldg(inp_feat + p);
-                    x = (inp_pos[3 * (size_t)p] - cx) * scale;
-                    y = (inp_pos[3 * (size_t)p + 1] - cy) * scale;
-                    z = (inp_pos[3 * (size_t)p + 2] - cz) * scale;
-                    const float nrm = sqrtf(x * x + y * y + z * z);
-                    const float amax = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
-                    const float stretch = amax < 1e-8f ? 0.f : 0.5f * nrm / amax;
-                    x = fminf(fmaxf((x * stretch + ox + 0.5f) * sm1, 0.f), sm1);
-                    y = fminf(fmaxf((y * stretch + oy + 0.5f) * sm1, 0.f), sm1);
-                    z = fminf(fmaxf((z * stretch + oz + 0.5f) * sm1, 0.f), sm1);
-                    f.x *= imp;
-                    f.y *= imp;
-                    f.z *= imp;
-                    f.w *= imp;
-                }
-                // sum of the neighbour importances, in list order like the reference
-                for (int j = 0; j < cnt; ++j) norm += __shfl_sync(0xffffffffu, nimp_l, j);
-                // ---- phase B: lane = tap x channel
-                for (int j = 0; j < cnt; ++j) {
-                    const float xj = __shfl_sync(0xffffffffu, x, j), yj = __shfl_sync(0xffffffffu, y, j),
-                                zj = __shfl_sync(0xffffffffu, z, j);
-                    const float f0 = __shfl_sync(0xffffffffu, f.x, j), f1 = __shfl_sync(0xffffffffu, f.y, j),
-                                f2 = __shfl_sync(0xffffffffu, f.z, j), f3 = __shfl_sync(0xffffffffu, f.w, j);
-                    const float fj = ch == 0 ? f0 : ch == 1 ? f1 : ch == 2 ? f2 : f3;
-                    const int x0 = min((int)xj, S - 1), y0 = min((int)yj, S - 1), z0 = min((int)zj, S - 1);
-                    const float ax = xj - (float)x0, ay = yj - (float)y0, az = zj - (float)z0;
-                    // a "+1" tap that is clamped onto its "+0" twin carries weight 0: skip
-                    const bool dup = (tx && x0 == S - 1) || (ty && y0 == S - 1) || (tz && z0 == S - 1);
-                    if (!dup) {
-                        const float w = (tx ? ax : 1.f - ax) * (ty ? ay : 1.f - ay) * (tz ? az : 1.f - az);
-                        const int cell = ((z0 + tz) * S + (y0 + ty)) * S + (x0 + tx);
-                        B[cell * 4 + ch] += w * fj;
-                    }
-                    __syncwarp();
-                }
-            }
-        }
+    const long long nwarps = (long long)gridDim.x * kCc4Warps;
+    long long gv[kCcGroup];
+    float gnorm[kCcGroup];
+    int g = 0;
+    auto flush = [&]() {
+        // out[gv[i], :] = act(B_i . W / norm_i + bias) for the g collected voxels
         for (int oc = lane; oc < Cout; oc += 32) {
-            float acc = 0.f;
-            if (e > b) {
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
-                for (int j = 0; j < K; j += 4) {
-                    const float4 bv = *reinterpret_cast<const float4*>(B + j);
-                    a0 = fmaf(bv.x, Ws[(j + 0) * Cout + oc], a0);
-                    a1 = fmaf(bv.y, Ws[(j + 1) * Cout + oc], a1);
-                    a2 = fmaf(bv.z, Ws[(j + 2) * Cout + oc], a2);
-                    a3 = fmaf(bv.w, Ws[(j + 3) * Cout + oc], a3);
+            float acc[kCcGroup];
+#pragma unroll
+            for (int i = 0; i < kCcGroup; ++i) acc[i] = 0.f;
+#pragma unroll 2
+            for (int j = 0; j < K; j += 4) {
+                const float w0 = Ws[(j + 0) * Cout + oc], w1 = Ws[(j + 1) * Cout + oc], w2 = Ws[(j + 2) * Cout + oc],
+                            w3 = Ws[(j + 3) * Cout + oc];
+#pragma unroll
+                for (int i = 0; i < kCcGroup; ++i) {
+                    if (i < g) {
+                        const float4 bv = *reinterpret_cast<const float4*>(Bw + i * K + j);
+                        acc[i] = fmaf(bv.x, w0, acc[i]);
+                        acc[i] = fmaf(bv.y, w1, acc[i]);
+                        acc[i] = fmaf(bv.z, w2, acc[i]);
+                        acc[i] = fmaf(bv.w, w3, acc[i]);
+                    }
                 }
-                acc = (a0 + a1) + (a2 + a3);
-                if (normalize && norm != 0.f) acc /= norm;
             }
-            if (bias) acc += bias[oc];
-            if (relu) acc = fmaxf(acc, 0.f);
-            out[(size_t)v * Cout + oc] = acc;
+#pragma unroll
+            for (int i = 0; i < kCcGroup; ++i) {
+                if (i < g) {
+                    float r = acc[i];
+                    if (normalize && gnorm[i] != 0.f) r /= gnorm[i];
+                    if (bias) r += bias[oc];
+                    if (relu) r = fmaxf(r, 0.f);
+                    out[(size_t)gv[i] * Cout + oc] = r;
+                }
+            }
         }
         __syncwarp();
+        g = 0;
+    };
+    for (long long v = blockIdx.x * (long long)kCc4Warps + warp; v < V; v += nwarps) {
+        const int64_t b = splits[v], e = splits[v + 1];
+        if (e <= b) {
+            for (int oc = lane; oc < Cout; oc += 32) {
+                float r = bias ? bias[oc] : 0.f;
+                if (relu) r = fmaxf(r, 0.f);
+                out[(size_t)v * Cout + oc] = r;
+            }
+            continue;
+        }
+        float* B = Bw + g * K;
+        for (int j = lane; j < K; j += 32) B[j] = 0.f;
+        __syncwarp();
+        float norm = 0.f;
+        const float cx = out_pos[3 * v], cy = out_pos[3 * v + 1], cz = out_pos[3 * v + 2];
+        const float scale = 2.0f / extents[v * extents_stride];
+        for (int64_t n0 = b; n0 < e; n0 += 32) {
+            const int cnt = (int)min((int64_t)32, e - n0);
+            // ---- phase A: lane = neighbour
+            float x = 0.f, y = 0.f, z = 0.f, imp = 0.f, nimp_l = 0.f;
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < cnt) {
+                const int p = nidx[n0 + lane];
+                nimp_l = nimp ? nimp[n0 + lane] : 1.0f;
+                imp = inp_importance ? nimp_l * inp_importance[p] : nimp_l;
+                f = __ldg(inp_feat + p);
+                x = (inp_pos[3 * (size_t)p] - cx) * scale;
+                y = (inp_pos[3 * (size_t)p + 1] - cy) * scale;
+                z = (inp_pos[3 * (size_t)p + 2] - cz) * scale;
+                const float nrm = sqrtf(x * x + y * y + z * z);
+                const float amax = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+                const float stretch = amax < 1e-8f ? 0.f : 0.5f * nrm / amax;
+                x = fminf(fmaxf((x * stretch + ox + 0.5f) * sm1, 0.f), sm1);
+                y = fminf(fmaxf((y * stretch + oy + 0.5f) * sm1, 0.f), sm1);
+                z = fminf(fmaxf((z * stretch + oz + 0.5f) * sm1, 0.f), sm1);
+                f.x *= imp;
+                f.y *= imp;
+                f.z *= imp;
+                f.w *= imp;
+            }
+            // sum of the neighbour importances, in list order like the reference
+            for (int j = 0; j < cnt; ++j) norm += __shfl_sync(0xffffffffu, nimp_l, j);
+            // ---- phase B: lane = tap x channel
+            for (int j = 0; j < cnt; ++j) {
+                const float xj = __shfl_sync(0xffffffffu, x, j), yj = __shfl_sync(0xffffffffu, y, j),
+                            zj = __shfl_sync(0xffffffffu, z, j);
+                const float f0 = __shfl_sync(0xffffffffu, f.x, j), f1 = __shfl_sync(0xffffffffu, f.y, j),
+                            f2 = __shfl_sync(0xffffffffu, f.z, j), f3 = __shfl_sync(0xffffffffu, f.w, j);
+                const float fj = ch == 0 ? f0 : ch == 1 ? f1 : ch == 2 ? f2 : f3;
+                const int x0 = min((int)xj, S - 1), y0 = min((int)yj, S - 1), z0 = min((int)zj, S - 1);
+                const float ax = xj - (float)x0, ay = yj - (float)y0, az = zj - (float)z0;
+                // a "+1" tap that is clamped onto its "+0" twin carries weight 0: skip
+                const bool dup = (tx && x0 == S - 1) || (ty && y0 == S - 1) || (tz && z0 == S - 1);
+                if (!dup) {
+                    const float w = (tx ? ax : 1.f - ax) * (ty ? ay : 1.f - ay) * (tz ? az : 1.f - az);
+                    const int cell = ((z0 + tz) * S + (y0 + ty)) * S + (x0 + tx);
+                    B[cell * 4 + ch] += w * fj;
+                }
+                __syncwarp();
+            }
+        }
+        // slot bookkeeping with compile-time register indices
+#pragma unroll
+        for (int i = 0; i < kCcGroup; ++i)
+            if (i == g) {
+                gv[i] = v;
+                gnorm[i] = norm;
+            }
+        if (++g == kCcGroup) flush();
     }
+    if (g > 0) flush();
 }
 
 // importance = scale_compat * clamp((1 - d2)^3, 0, 1)
@@ -199,12 +239,12 @@ void continuous_conv(const float* filters, const float* out_pos, const float* ex
                      int normalize, const float* bias, int relu, float* out, cudaStream_t s) {
     if (V == 0) return;
     if (Cin == 4 && S == 4 && ((uintptr_t)inp_feat % 16) == 0) {
-        const size_t smem4 = (size_t)(64 * 4 * Cout + kCcWarps * 64 * 4) * sizeof(float);
+        const size_t smem4 = (size_t)(64 * 4 * Cout + kCc4Warps * kCcGroup * 64 * 4) * sizeof(float);
         if (smem4 <= 160 * 1024) {
             ASRB_CUDA(cudaFuncSetAttribute(cconv4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
-            const unsigned blocks = (unsigned)std::min<size_t>(grid_for(V, kCcWarps), 148 * 4);
+            const unsigned blocks = (unsigned)std::min<size_t>(grid_for(V, kCc4Warps), 148 * 2);
             ProfileScope prof("continuous_conv", s, (double)V * 2.0 * 256 * Cout);
-            cconv4_kernel<4><<<blocks, kCcWarps * 32, smem4, s>>>(filters, out_pos, extents, extents_stride, offset, inp_pos,
+            cconv4_kernel<4><<<blocks, kCc4Warps * 32, smem4, s>>>(filters, out_pos, extents, extents_stride, offset, inp_pos,
                                                                  (const float4*)inp_feat, inp_importance, nidx, nimp,
                                                                  splits, V, Cout, normalize, bias, relu, out);
             ASRB_CHECK_LAUNCH();

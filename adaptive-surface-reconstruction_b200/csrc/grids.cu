@@ -63,7 +63,17 @@ __device__ __forceinline__ Probe make_probe(const Cell& c, int p) {
     return r;
 }
 
-constexpr int kProbes = 37;
+// A grid level is a set of non-overlapping voxels (octree leaves, then complete sibling
+// groups merged into their parent), so across one face a voxel sees EITHER a same-level
+// neighbour OR up to four finer ones OR one coarser one.  The probes therefore run in two
+// rounds: lanes 1..6 look up the same-level neighbours, and only the faces that came back
+// empty (~20 %) issue their 4 finer + 1 coarser probes (lanes 0..29 of the second round).
+// The reference probes all 55 slots unconditionally (grid.cpp:102-170); the result is the
+// same table (bit-exact parity tests, incl. the margin-free boxes with their junk leaves).
+__device__ __forceinline__ int second_round_face(int lane) {  // lane 0..29 -> probe 7..36 -> face
+    const int p = lane + 7;
+    return p < 31 ? (p - 7) >> 2 : p - 31;
+}
 
 // pass 1: 55-bit slot mask per voxel
 __global__ void __launch_bounds__(256)
@@ -73,13 +83,16 @@ adjacency_mask_kernel(const Key* __restrict__ keys, long long V, const KeyTableV
     const int lane = threadIdx.x & 31;
     if (w >= V) return;
     const Cell c = key_cell(keys[w]);
-    unsigned long long m = 0;
-    for (int p = lane; p < kProbes; p += 32) {
-        if (p == 0) {
-            m |= 1ULL;
-            continue;
-        }
-        const Probe pr = make_probe(c, p);
+    unsigned long long m = lane == 0 ? 1ULL : 0ULL;
+    bool same = false;
+    if (lane >= 1 && lane < 7) {
+        const Probe pr = make_probe(c, lane);
+        same = pr.key && table_find(table, pr.key) >= 0;
+        if (same) m = 1ULL << lane;
+    }
+    const unsigned same_faces = __ballot_sync(0xffffffffu, same) >> 1;  // bit f = face f has a same-level neighbour
+    if (lane < 30 && !((same_faces >> second_round_face(lane)) & 1)) {
+        const Probe pr = make_probe(c, lane + 7);
         if (pr.key && table_find(table, pr.key) >= 0) m |= 1ULL << pr.slot;
     }
     unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)m);
@@ -91,7 +104,7 @@ adjacency_mask_kernel(const Key* __restrict__ keys, long long V, const KeyTableV
     }
 }
 
-// pass 2: write (index, slot) in slot order
+// pass 2: write (index, slot) in slot order; only the slots present in the mask are looked up
 __global__ void __launch_bounds__(256)
 adjacency_fill_kernel(const Key* __restrict__ keys, long long V, const KeyTableView table,
                       const unsigned long long* __restrict__ mask, const int64_t* __restrict__ splits,
@@ -99,23 +112,30 @@ adjacency_fill_kernel(const Key* __restrict__ keys, long long V, const KeyTableV
     const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= V) return;
-    const Cell c = key_cell(keys[w]);
     const unsigned long long m = mask[w];
+    const Cell c = key_cell(keys[w]);
     const int64_t base = splits[w];
-    for (int p = lane; p < kProbes; p += 32) {
-        long long idx = -1;
-        int slot = 0;
-        if (p == 0) {
-            idx = w;
-        } else {
-            const Probe pr = make_probe(c, p);
-            slot = pr.slot;
-            if (pr.key && ((m >> slot) & 1)) idx = table_find(table, pr.key);
+    auto emit = [&](int slot, long long idx) {
+        const int pos = __popcll(m & ((1ULL << slot) - 1));
+        nidx[base + pos] = (int32_t)idx;
+        nslot[base + pos] = (uint8_t)slot;
+    };
+    if (lane == 0) emit(0, w);
+    if (lane >= 1 && lane < 7 && ((m >> lane) & 1)) emit(lane, table_find(table, make_probe(c, lane).key));
+    if (lane < 30 && (m >> 7)) {
+        const int p = lane + 7;
+        bool want;
+        if (p < 31) {
+            want = (m >> p) & 1;
+        } else {  // a coarser slot is one of 31 + 4 f + {0..3}: any bit of the face's nibble
+            want = (m >> (31 + 4 * (p - 31))) & 0xF;
         }
-        if (idx >= 0) {
-            const int pos = __popcll(m & ((1ULL << slot) - 1));
-            nidx[base + pos] = (int32_t)idx;
-            nslot[base + pos] = (uint8_t)slot;
+        if (want) {
+            const Probe pr = make_probe(c, p);
+            if (pr.key && ((m >> pr.slot) & 1)) {
+                const long long idx = table_find(table, pr.key);
+                if (idx >= 0) emit(pr.slot, idx);
+            }
         }
     }
 }

@@ -12,7 +12,8 @@
 // a query: 16 lanes binary-search the window bounds of the <= 2x2x2 cells (edge
 // >= 2r) that cover the query ball, then all 32 lanes stream the concatenated
 // windows with coalesced 16-byte loads, test the strict squared distance and
-// compact hits with ballot/popc.  count -> scan -> fill -> per-row rank sort.
+// compact hits with ballot/popc.  count -> scan -> fill with the per-row rank sort by
+// (d2, index) fused in (shared memory for rows of <= 32 hits).
 //
 // Squared distances are evaluated as ((dx*dx) + dy*dy) + dz*dz in fp32 without
 // FMA contraction, the order nanoflann's L2 adaptor uses for dim 3, so that the
@@ -213,9 +214,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 ball_query_kernel(const KeyTableView cells, const float4* __restrict__ spts, BinFrame f,
                   const float* __restrict__ queries, const float* __restrict__ radii, long long nq,
                   int32_t* __restrict__ counts, const int64_t* __restrict__ splits,
-                  unsigned long long* __restrict__ out_keys) {
+                  unsigned long long* __restrict__ out_keys, int32_t* __restrict__ out_idx,
+                  float* __restrict__ out_d2) {
     __shared__ unsigned s_begin[kWarpsPerBlock][32];
     __shared__ int s_pre[kWarpsPerBlock][33];
+    __shared__ unsigned long long s_hit[FILL ? kWarpsPerBlock : 1][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long q = blockIdx.x * (long long)kWarpsPerBlock + warp;
     if (q >= nq) return;
@@ -253,6 +256,10 @@ ball_query_kernel(const KeyTableView cells, const float4* __restrict__ spts, Bin
     const int total = __shfl_sync(0xffffffffu, pre, 31);
     int found = 0;
     const int64_t out_base = FILL ? splits[q] : 0;
+    // FILL: rows of <= 32 hits (the rule) are collected in shared memory and rank-sorted by
+    // (d2, index) right here; longer rows go through `out_keys` and are sorted below
+    const int row_n = FILL ? (int)(splits[q + 1] - out_base) : 0;
+    const bool small = row_n <= 32;
     for (int t0 = 0; t0 < total; t0 += 32) {
         const int t = t0 + lane;
         bool hit = false;
@@ -269,36 +276,34 @@ ball_query_kernel(const KeyTableView cells, const float4* __restrict__ spts, Bin
             key = ((unsigned long long)__float_as_uint(d2) << 32) | __float_as_uint(p.w);
         }
         const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (FILL && hit) out_keys[out_base + found + __popc(m & ((1u << lane) - 1))] = key;
+        if (FILL && hit) {
+            const int pos = found + __popc(m & ((1u << lane) - 1));
+            if (small) s_hit[warp][pos] = key;
+            else out_keys[out_base + pos] = key;
+        }
         found += __popc(m);
     }
-    if (!FILL && lane == 0) counts[q] = found;
-}
-
-// Per-row rank sort of the (d2, index) keys; keys are unique within a row.
-__global__ void __launch_bounds__(256)
-row_sort_kernel(const unsigned long long* __restrict__ keys, const int64_t* __restrict__ splits, long long nq,
-                int32_t* __restrict__ out_idx, float* __restrict__ out_d2) {
-    const long long q = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (q >= nq) return;
-    const int64_t b = splits[q];
-    const int n = (int)(splits[q + 1] - b);
-    if (n <= 32) {
-        const unsigned long long mine = lane < n ? keys[b + lane] : ~0ULL;
+    if (!FILL) {
+        if (lane == 0) counts[q] = found;
+        return;
+    }
+    __syncwarp();
+    if (small) {
+        const unsigned long long mine = lane < row_n ? s_hit[warp][lane] : ~0ULL;
         int rank = 0;
-        for (int j = 0; j < n; ++j) rank += __shfl_sync(0xffffffffu, mine, j) < mine ? 1 : 0;
-        if (lane < n) {
-            out_idx[b + rank] = (int32_t)(unsigned)mine;
-            out_d2[b + rank] = __uint_as_float((unsigned)(mine >> 32));
+        for (int j = 0; j < row_n; ++j) rank += __shfl_sync(0xffffffffu, mine, j) < mine ? 1 : 0;
+        if (lane < row_n) {
+            out_idx[out_base + rank] = (int32_t)(unsigned)mine;
+            out_d2[out_base + rank] = __uint_as_float((unsigned)(mine >> 32));
         }
     } else {
-        for (int i = lane; i < n; i += 32) {
-            const unsigned long long mine = keys[b + i];
+        __threadfence_block();  // this warp's own key writes, read back by all its lanes
+        for (int i = lane; i < row_n; i += 32) {
+            const unsigned long long mine = out_keys[out_base + i];
             int rank = 0;
-            for (int j = 0; j < n; ++j) rank += __ldg(keys + b + j) < mine ? 1 : 0;
-            out_idx[b + rank] = (int32_t)(unsigned)mine;
-            out_d2[b + rank] = __uint_as_float((unsigned)(mine >> 32));
+            for (int j = 0; j < row_n; ++j) rank += out_keys[out_base + j] < mine ? 1 : 0;
+            out_idx[out_base + rank] = (int32_t)(unsigned)mine;
+            out_d2[out_base + rank] = __uint_as_float((unsigned)(mine >> 32));
         }
     }
 }
@@ -403,7 +408,8 @@ void search_prepare(Search& S, const float* d_points, int64_t n, const float* d_
     if (nq > 0) {
         ProfileScope prof("ball_query_count", s);
         ball_query_kernel<false><<<grid_for(nq, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
-                S.cells.view(), (const float4*)S.spts.get(), f, d_queries, d_radii, nq, counts.get(), nullptr, nullptr);
+                S.cells.view(), (const float4*)S.spts.get(), f, d_queries, d_radii, nq, counts.get(), nullptr, nullptr, nullptr,
+                nullptr);
         ASRB_CHECK_LAUNCH();
     }
     exclusive_sum_i32_to_i64(counts.get(), S.splits.get(), (size_t)nq, s);
@@ -418,9 +424,8 @@ void search_fill(Search& S, int32_t* d_idx, float* d_d2, int64_t* d_splits, cuda
     DevBuf<unsigned long long> keys((size_t)S.num_pairs, s);
     ProfileScope prof("ball_query_fill_sort", s);
     ball_query_kernel<true><<<grid_for(S.nq, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
-            S.cells.view(), (const float4*)S.spts.get(), f, S.queries, S.radii, S.nq, nullptr, S.splits.get(), keys.get());
-    ASRB_CHECK_LAUNCH();
-    row_sort_kernel<<<grid_for((size_t)S.nq * 32, 256), 256, 0, s>>>(keys.get(), S.splits.get(), S.nq, d_idx, d_d2);
+            S.cells.view(), (const float4*)S.spts.get(), f, S.queries, S.radii, S.nq, nullptr, S.splits.get(), keys.get(),
+            d_idx, d_d2);
     ASRB_CHECK_LAUNCH();
 }
 
