@@ -7,9 +7,9 @@ reference, the work happens on the current CUDA device.
 
 In scope (hot path): create_octree, create_grids_from_octree,
 create_dual_vertex_indices, reconstruct_surface (octree-conv -> SDF -> vertices).
-Rows §8 marks "next" and that are not built yet raise NotImplementedError instead
-of silently running elsewhere: KDTree (f-2), remove_connected_components (f-3),
-triangle connectivity of reconstruct_surface (f-1, returned empty with a warning).
+The "next" rows f-1 (triangle connectivity) and f-3 (remove_connected_components) are built
+on the GPU as well; f-2 (KDTree: radius estimation / density pre-filter) is not built yet and
+raises NotImplementedError instead of silently running elsewhere.
 """
 import os
 import warnings
@@ -110,9 +110,8 @@ def reconstruct_surface(points, normals, radii, point_radius_scale=1.0, density_
     (asr.cpp:95-349).  Runs the hot path (grid building, aggregation search,
     aggregate/unet/decode, dual-contouring vertices) on the GPU.
 
-    Not built yet (SURVEY.md §8f "next" rows): the kNN radius estimation / density
-    pre-filter (radii must be given; density_percentile_threshold is ignored) and
-    the triangle connectivity (returned empty) / connected-component filter.
+    Not built yet: the kNN radius estimation / density pre-filter
+    (radii must be given; density_percentile_threshold is ignored).
     `model` (an asr_b200.model.UNet) overrides the model.pt lookup."""
     points = _f32(points, "points", "points must have shape [num_points,3]", 2, 3)
     normals = np.ascontiguousarray(normals, dtype=np.float32)
@@ -127,21 +126,29 @@ def reconstruct_surface(points, normals, radii, point_radius_scale=1.0, density_
         raise NotImplementedError("radius estimation (KDTree.compute_k_radius, SURVEY.md §8f-2) is not built yet: "
                                   "pass per-point radii")
     net = model if model is not None else _load_model()
-    out = _pipeline.reconstruct_vertices_host(net, points, normals, radii, radius_scale=float(point_radius_scale),
-                                              max_depth=int(octree_max_depth),
-                                              contouring_value_threshold=float(contouring_value_threshold))
-    warnings.warn("asr_b200.reconstruct_surface: triangle extraction (SURVEY.md §8f-1) is not built yet; "
-                  "'triangles' is empty", RuntimeWarning)
-    return {"vertices": out["vertices"], "triangles": np.zeros((0, 3), np.int32)}
+    dev = torch.device("cuda")
+    p = torch.from_numpy(points).to(dev)
+    out = _pipeline.reconstruct_vertices(net, p, torch.from_numpy(normals).to(dev), torch.from_numpy(radii).to(dev),
+                                         points.min(0), points.max(0), radius_scale=float(point_radius_scale),
+                                         max_depth=int(octree_max_depth),
+                                         contouring_value_threshold=float(contouring_value_threshold), triangles=True)
+    # asr.cpp:343-345: RemoveConnectedComponents with the caller's limits
+    v, t = _ops.remove_connected_components(out["vertices"], out["triangles"], int(keep_n_connected_components),
+                                            int(minimum_component_size))
+    return {"vertices": v.cpu().numpy(), "triangles": t.cpu().numpy()}
 
 
 def remove_connected_components(vertices, triangles, keep_n_largest_components, minimum_component_size=3):
-    """module.cpp:348-350 — post-process row f-3, outside the hot path."""
+    """module.cpp:348-350 / pyRemoveConnectedComponents :111-142 (row f-3)."""
     vertices = _f32(vertices, "vertices", "vertices must have shape [N,3]", 2, 3)
     triangles = np.ascontiguousarray(triangles, dtype=np.int32)
     if triangles.ndim != 2 or triangles.shape[1] != 3:
         raise ValueError("triangles must have shape [N,3]")
-    raise NotImplementedError("remove_connected_components (SURVEY.md §8f-3) is not built yet")
+    if triangles.size and (triangles.min() < 0 or triangles.max() >= vertices.shape[0]):
+        raise RuntimeError("triangle index out of range")  # std::out_of_range in the reference
+    v, t = _ops.remove_connected_components(torch.from_numpy(vertices).cuda(), torch.from_numpy(triangles).cuda(),
+                                            int(keep_n_largest_components), int(minimum_component_size))
+    return {"vertices": v.cpu().numpy(), "triangles": t.cpu().numpy()}
 
 
 class KDTree:

@@ -59,6 +59,10 @@ SIGNATURES = {
     "asr_dense_tf32x3": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp]),
     "asr_contour_count": (_i32, [_vp, _vp, _i64, _f32, _vp, _vp, _pi64, _vp]),
     "asr_contour_fill": (_i32, [_vp, _vp, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "asr_contour_triangles_create": (_i32, [_vp, _vp, _i64, _f32, _vp, _i64, _i64, _vp, _pp, _pi64, _pi64]),
+    "asr_contour_triangles_fill": (_i32, [_vp, _vp, _vp, _vp]),
+    "asr_contour_triangles_destroy": (None, [_vp]),
+    "asr_mesh_components": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -429,3 +429,56 @@ def contour_vertices(values, dual_indices, node_positions, unsigned_threshold=1.
     check(L.asr_contour_fill(_ptr(values), _ptr(duals), D, float(unsigned_threshold), _ptr(pos), _ptr(flag),
                              _ptr(offset), _ptr(verts), _ptr(vdual), _stream()))
     return verts, vdual
+
+
+def contour_mesh(values, dual_indices, node_positions, unsigned_threshold=1.0):
+    """CreateTriangleMesh (contouring.cpp:29-460) on the GPU.  Returns (vertices f32[M + X, 3],
+    triangles i32[T, 3], dual index of the first M vertices i64[M]); X = fan-centre vertices."""
+    verts, vdual = contour_vertices(values, dual_indices, node_positions, unsigned_threshold)
+    values = _cuda(values, torch.float32, "values")
+    duals = _cuda(dual_indices, torch.int64, "dual_indices")
+    M = verts.shape[0]
+    L = lib()
+    h, T, X = C.c_void_p(0), _i64(0), _i64(0)
+    check(L.asr_contour_triangles_create(_ptr(values), _ptr(duals), duals.shape[0], float(unsigned_threshold),
+                                         _ptr(vdual), M, values.shape[0], _stream(), C.byref(h), C.byref(T),
+                                         C.byref(X)))
+    try:
+        allv = torch.empty((M + X.value, 3), dtype=torch.float32, device=verts.device)
+        allv[:M] = verts
+        tris = torch.empty((T.value, 3), dtype=torch.int32, device=verts.device)
+        check(L.asr_contour_triangles_fill(h, _ptr(allv), _ptr(tris), _stream()))
+    finally:
+        L.asr_contour_triangles_destroy(h)
+    return allv, tris, vdual
+
+
+def remove_connected_components(vertices, triangles, keep_n_largest_components, minimum_component_size=3):
+    """RemoveConnectedComponents (postprocess.cpp:143-201): keep the `keep_n` largest vertex
+    components (ties: the later component first, std::greater on (size, id)) that have at least
+    `minimum_component_size` vertices; vertices keep their order, triangles are re-indexed.
+    The labelling runs in asr_mesh_components; the selection below is index plumbing."""
+    vertices = _cuda(vertices, torch.float32, "vertices")
+    tris = _cuda(triangles, torch.int32, "triangles")
+    if vertices.ndim != 2 or vertices.shape[1] != 3:
+        raise ValueError("vertices must have shape [N,3]")
+    if tris.ndim != 2 or tris.shape[1] != 3:
+        raise ValueError("triangles must have shape [N,3]")
+    V = vertices.shape[0]
+    if V == 0:
+        return vertices, tris
+    label = torch.empty(V, dtype=torch.int64, device=vertices.device)
+    size = torch.empty(V, dtype=torch.int64, device=vertices.device)
+    check(lib().asr_mesh_components(_ptr(tris), tris.shape[0], V, _ptr(label), _ptr(size), _stream()))
+    roots = torch.nonzero(size > 0).reshape(-1)  # ascending = the reference's component ids
+    order = torch.argsort(size[roots] * (V + 1) + roots, descending=True)
+    keep_n = int(min(int(keep_n_largest_components), roots.numel())) if keep_n_largest_components > 0 else 0
+    chosen = roots[order[:keep_n]]
+    chosen = chosen[size[chosen] >= int(minimum_component_size)]
+    keep_root = torch.zeros(V, dtype=torch.bool, device=vertices.device)
+    keep_root[chosen] = True
+    mask = keep_root[label]
+    new_index = torch.cumsum(mask, 0, dtype=torch.int64) - 1
+    tl = tris.long()
+    tmask = mask[tl[:, 0]] & mask[tl[:, 1]] & mask[tl[:, 2]]
+    return vertices[mask].contiguous(), new_index[tl[tmask]].to(torch.int32).contiguous()

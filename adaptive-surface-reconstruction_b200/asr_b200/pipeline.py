@@ -81,9 +81,11 @@ def run_network(model, input_dict, timer=None):
 
 
 def reconstruct_vertices(model, points, normals, radii, bb_min=None, bb_max=None, levels=None, radius_scale=1.0,
-                         max_depth=21, contouring_value_threshold=1.0, timer=None):
+                         max_depth=21, contouring_value_threshold=1.0, timer=None, triangles=False):
     """Whole path on device tensors.  bb defaults to the exact min/max of the
-    points like the C++ driver (asr.cpp:148-150)."""
+    points like the C++ driver (asr.cpp:148-150).  triangles=True also runs the polygon
+    passes of CreateTriangleMesh: the result then has "triangles"
+    and "vertices" includes the fan-centre vertices after the dual-cell vertices."""
     timer = timer or StageTimer()
     levels = levels or model.octree_levels
     if bb_min is None:
@@ -93,10 +95,17 @@ def reconstruct_vertices(model, points, normals, radii, bb_min=None, bb_max=None
     d, duals, tree = build_input_dict(points, normals, radii, bb_min, bb_max, levels, radius_scale, max_depth, timer, K)
     values = run_network(model, d, timer)
     timer.start()
-    verts, vdual = K.contour_vertices(values, duals, d["voxel_centers0"], contouring_value_threshold)
+    tris = None
+    if triangles:
+        verts, tris, vdual = K.contour_mesh(values, duals, d["voxel_centers0"], contouring_value_threshold)
+    else:
+        verts, vdual = K.contour_vertices(values, duals, d["voxel_centers0"], contouring_value_threshold)
     timer.lap("contour")
-    return {"vertices": verts, "vertex_dual": vdual, "values": values, "dual_vertex_indices": duals,
-            "input_dict": d, "octree": tree}
+    out = {"vertices": verts, "vertex_dual": vdual, "values": values, "dual_vertex_indices": duals,
+           "input_dict": d, "octree": tree}
+    if tris is not None:
+        out["triangles"] = tris
+    return out
 
 
 _PINNED = {}
@@ -126,5 +135,9 @@ def reconstruct_vertices_host(model, points, normals, radii, bb_min=None, bb_max
         bb_min, bb_max = points.min(0), points.max(0)
     out = reconstruct_vertices(model, p, n, r, bb_min, bb_max, **kw)
     v, s = _to_host(out["vertices"], "vertices"), _to_host(out["values"], "values")
+    t = _to_host(out["triangles"], "triangles") if "triangles" in out else None
     torch.cuda.current_stream().synchronize()
-    return {"vertices": v.numpy().copy(), "values": s.numpy().copy()}
+    res = {"vertices": v.numpy().copy(), "values": s.numpy().copy()}
+    if t is not None:
+        res["triangles"] = t.numpy().copy()
+    return res

@@ -22,6 +22,13 @@ void contour_count(const float* values, const int64_t* duals, int64_t D, float t
                    int64_t* num_vertices, cudaStream_t s);
 void contour_fill(const float* values, const int64_t* duals, int64_t D, float thr, const float* pos,
                   const uint8_t* flag, const int64_t* offset, float* vertices, int64_t* vertex_dual, cudaStream_t s);
+struct TriPlan;
+TriPlan* contour_triangles_create(const float* values, const int64_t* duals, int64_t D, float thr,
+                                  const int64_t* vertex_dual, int64_t M, int64_t V, int64_t* num_triangles,
+                                  int64_t* num_extra, cudaStream_t s);
+void contour_triangles_fill(TriPlan& P, float* vertices, int32_t* triangles, cudaStream_t s);
+void contour_triangles_destroy(TriPlan* P);
+void mesh_components(const int32_t* triangles, int64_t T, int64_t V, int64_t* label, int64_t* size, cudaStream_t s);
 size_t packed_weights_floats(int K, int N);
 void pack_weights(const float* W, int K, int N, float* out, cudaStream_t s);
 void dense_gemm_tf32x3(const float* A, int64_t M, int K, int lda, const float* Wp, int N, const float* bias, int relu,
@@ -334,6 +341,33 @@ int asr_contour_count(const float* values, const int64_t* duals, int64_t D, floa
 int asr_contour_fill(const float* values, const int64_t* duals, int64_t D, float thr, const float* pos,
                      const uint8_t* flag, const int64_t* offset, float* vertices, int64_t* vertex_dual, void* stream) {
     return guarded([&] { contour_fill(values, duals, D, thr, pos, flag, offset, vertices, vertex_dual, S(stream)); });
+}
+
+int asr_contour_triangles_create(const float* values, const int64_t* duals, int64_t D, float thr,
+                                 const int64_t* vertex_dual, int64_t M, int64_t num_nodes, void* stream, void** handle,
+                                 int64_t* num_triangles, int64_t* num_extra_vertices) {
+    return guarded([&] {
+        ASRB_REQUIRE(handle && num_triangles && num_extra_vertices, "null argument");
+        ASRB_REQUIRE(D >= 0 && M >= 0 && num_nodes >= 0, "negative size");
+        *handle = contour_triangles_create(values, duals, D, thr, vertex_dual, M, num_nodes, num_triangles,
+                                           num_extra_vertices, S(stream));
+    });
+}
+int asr_contour_triangles_fill(void* handle, float* vertices, int32_t* triangles, void* stream) {
+    return guarded([&] {
+        ASRB_REQUIRE(handle, "null handle");
+        contour_triangles_fill(*static_cast<TriPlan*>(handle), vertices, triangles, S(stream));
+    });
+}
+void asr_contour_triangles_destroy(void* handle) { contour_triangles_destroy(static_cast<TriPlan*>(handle)); }
+
+int asr_mesh_components(const int32_t* triangles, int64_t num_triangles, int64_t num_vertices, int64_t* label,
+                        int64_t* size, void* stream) {
+    return guarded([&] {
+        ASRB_REQUIRE(num_triangles >= 0 && num_vertices >= 0, "negative size");
+        ASRB_REQUIRE(label || num_vertices == 0, "null argument");
+        mesh_components(triangles, num_triangles, num_vertices, label, size, S(stream));
+    });
 }
 
 }  // extern "C"

@@ -198,6 +198,32 @@ int asr_contour_fill(const float* d_values, const int64_t* d_dual_indices, int64
                      float unsigned_threshold, const float* d_node_positions, const uint8_t* d_flag,
                      const int64_t* d_offset, float* d_vertices, int64_t* d_vertex_dual, void* stream);
 
+/* ---------------------------------------------------------------- dual contouring (triangles)
+ * replaces the polygon passes of asr::CreateTriangleMesh, cpp/lib/contouring.cpp:202-459: one
+ * polygon per sign-changing primal edge, built from the crossing dual cells around it (1 triangle,
+ * 2 triangles split along the shorter diagonal, or a fan around an extra centre vertex).
+ * d_vertex_dual [M] is the output of asr_contour_fill.  _create returns the number of triangles T
+ * and of extra (fan centre) vertices X; _fill takes d_vertices [(M + X), 3] whose first M rows
+ * hold the dual-cell vertices, appends the X centre vertices and writes d_triangles [T, 3]
+ * (int32, emission order of the reference: vertex-major, edge-minor; the rotation of each
+ * triangle / fan is unspecified in the reference, see contour_tri.cu).  The value / dual /
+ * vertex_dual buffers passed to _create must stay valid until _fill. */
+int asr_contour_triangles_create(const float* d_values, const int64_t* d_dual_indices, int64_t num_duals,
+                                 float unsigned_threshold, const int64_t* d_vertex_dual, int64_t num_vertices,
+                                 int64_t num_nodes, void* stream, void** handle, int64_t* num_triangles,
+                                 int64_t* num_extra_vertices);
+int asr_contour_triangles_fill(void* handle, float* d_vertices, int32_t* d_triangles, void* stream);
+void asr_contour_triangles_destroy(void* handle);
+
+/* ---------------------------------------------------------------- mesh post-processing
+ * replaces asr::ConnectedComponents (cpp/lib/postprocess.cpp:81-141), the core of
+ * RemoveConnectedComponents (:143-176; python remove_connected_components, module.cpp:348).
+ * d_label [V]: smallest vertex index of the vertex' component (orders components like the
+ * reference's first-visit numbering); d_size [V] (optional): component size at the label's
+ * index, 0 elsewhere.  Out-of-range triangle indices -> status 2. */
+int asr_mesh_components(const int32_t* d_triangles, int64_t num_triangles, int64_t num_vertices, int64_t* d_label,
+                        int64_t* d_size, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -126,3 +126,66 @@ def test_contour_vertices_bit_exact(name, cloud, levels, geom_checkers):
         if reflib.available():
             m = reflib.create_triangle_mesh(vals, duals.cpu().numpy().astype(np.uint64), c, thr)
             assert np.array_equal(m["vertices"][:len(pv)], v.cpu().numpy())
+
+
+def _norm_tris(t):
+    """Rotation-normalised triangle multiset: each triangle starts with its smallest index,
+    cyclic order (= orientation) preserved; rows sorted."""
+    t = np.asarray(t, np.int64).reshape(-1, 3)
+    k = np.argmin(t, 1)
+    r = np.stack([t[np.arange(len(t)), (k + i) % 3] for i in range(3)], 1)
+    return r[np.lexsort((r[:, 2], r[:, 1], r[:, 0]))]
+
+
+@pytest.mark.parametrize("name,cloud,levels", list(small_clouds())[:3], ids=lambda x: x if isinstance(x, str) else None)
+def test_contour_triangles_match_reference(name, cloud, levels):
+    """Triangle part of CreateTriangleMesh (contouring.cpp:202-459) against the compiled
+    reference: same triangle multiset up to the rotation of each polygon (the reference starts
+    every cycle at a hash-order dependent dual), same fan-centre vertices to float rounding."""
+    from asr_b200 import ops
+    from oracle import reflib
+    if not reflib.available():
+        pytest.skip("compiled reference (oracle/_ref) not present")
+    t = _build(cloud)
+    g = t.grids(1, True)[0]
+    duals = t.dual_vertex_indices()
+    c = g["voxel_centers"].cpu().numpy()
+    s = g["voxel_sizes"].cpu().numpy()
+    rng = np.random.default_rng(11)
+    centre = c.mean(0)
+    rad = np.linalg.norm(c - centre, axis=1)
+    dist = rad - 0.9 * np.median(rad) + 0.05 * np.sin(9 * c[:, 0])
+    vals = np.stack([dist, np.abs(dist) / s * rng.uniform(0.5, 1.5, len(s))], 1).astype(np.float32)
+    for thr in (1.0, 0.4):
+        v, tri, vd = ops.contour_mesh(dev(vals), duals, g["voxel_centers"], thr)
+        m = reflib.create_triangle_mesh(vals, duals.cpu().numpy().astype(np.uint64), c, thr)
+        M = vd.shape[0]
+        assert v.shape[0] == m["vertices"].shape[0] and tri.shape[0] == m["triangles"].shape[0] > 50
+        assert np.array_equal(v[:M].cpu().numpy(), m["vertices"][:M])
+        assert np.abs(v[M:].cpu().numpy() - m["vertices"][M:]).max(initial=0.0) <= 1e-6
+        a, b = _norm_tris(tri.cpu().numpy()), _norm_tris(m["triangles"])
+        same = (a == b).all(1)
+        # a quad whose diagonals are equal to rounding may be split the other way
+        assert same.mean() > 0.999, "triangle sets differ: %d of %d" % ((~same).sum(), len(a))
+
+
+def test_remove_connected_components_matches_reference():
+    from asr_b200 import ops
+    from oracle import reflib
+    if not reflib.available():
+        pytest.skip("compiled reference (oracle/_ref) not present")
+    rng = np.random.default_rng(3)
+    # a handful of separate strips of different sizes + isolated vertices
+    verts, tris, base = [], [], 0
+    for n in (40, 7, 7, 3, 12, 1, 1, 25):
+        verts.append(rng.standard_normal((n, 3)).astype(np.float32))
+        for i in range(n - 2):
+            tris.append([base + i, base + i + 1, base + i + 2])
+        base += n
+    verts = np.concatenate(verts)
+    tris = np.asarray(tris, np.int32)[rng.permutation(len(tris))]
+    for keep, mins in ((np.iinfo(np.int64).max, 3), (3, 3), (2, 1), (4, 8), (1, 100), (100, 1)):
+        ref = reflib.remove_connected_components(verts, tris, keep, mins)
+        v, t = ops.remove_connected_components(dev(verts), dev(tris), keep, mins)
+        assert np.array_equal(v.cpu().numpy(), ref["vertices"]), (keep, mins)
+        assert np.array_equal(t.cpu().numpy(), ref["triangles"]), (keep, mins)

@@ -37,12 +37,18 @@ def test_reconstruct_surface_drop_in():
     from asr_b200 import clouds, model
     c = clouds.sphere(6000, seed=2)
     net = model.seeded_weights(model.UNet(5), seed=4).cuda()
-    with pytest.warns(RuntimeWarning):
-        mesh = asr.reconstruct_surface(c["points"], c["normals"], c["radii"], model=net,
-                                       contouring_value_threshold=1e9)
+    mesh = asr.reconstruct_surface(c["points"], c["normals"], c["radii"], model=net, contouring_value_threshold=1e9)
     assert set(mesh) == {"vertices", "triangles"}
     assert mesh["vertices"].dtype == np.float32 and mesh["vertices"].shape[1] == 3
     assert mesh["triangles"].dtype == np.int32 and mesh["triangles"].shape[1] == 3
+    # random weights give an arbitrary SDF: only the structure is checked here (the triangle and
+    # component passes are compared with the reference in test_gpu_geometry.py).  Every vertex that
+    # survives the default component filter (>= 3 vertices) is used by a triangle.
+    assert len(np.unique(mesh["triangles"])) == mesh["vertices"].shape[0]
+    if mesh["triangles"].size:
+        assert mesh["triangles"].min() >= 0 and mesh["triangles"].max() < mesh["vertices"].shape[0]
+    out = asr.remove_connected_components(mesh["vertices"], mesh["triangles"], 1)
+    assert out["vertices"].shape[0] <= mesh["vertices"].shape[0] and out["triangles"].shape[1] == 3
     with pytest.raises(RuntimeError):
         asr.reconstruct_surface(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), np.zeros(0, np.float32),
                                 model=net)
