@@ -203,7 +203,7 @@ class UNet(torch.nn.Module):
             skips.append(x)
         for l in range(L - 2, -1, -1):
             x, _ = getattr(self, "sparseconv_up%d" % l).run(x, P["up"][l], None, K)
-            x = torch.cat([x, skips[l]], -1) if l >= 1 else x + skips[0]
+            x = K.cat([x, skips[l]], -1) if l >= 1 else K.add(x, skips[0])
             x, _ = getattr(self, "sparseconv_decblock%d" % l).run(x, P["nb"][l], None, K)
         return x
 

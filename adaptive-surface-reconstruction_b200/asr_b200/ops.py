@@ -252,6 +252,16 @@ def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_
     return out
 
 
+def cat(tensors, dim=-1):
+    """Channel concatenation of the U-Net's skip connections (the sharded namespace keeps its
+    row-validity bookkeeping here)."""
+    return torch.cat(tensors, dim)
+
+
+def add(x, y):
+    return x + y
+
+
 class ConvPlan:
     """Slot-sorted form of one neighbour table; build once, reuse for every conv on it."""
 

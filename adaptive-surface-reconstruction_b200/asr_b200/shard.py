@@ -1,28 +1,30 @@
 """Multi-GPU execution of the hot path on one node: one process per GPU,
 `torch.distributed` (NCCL over NVLink / NVSwitch) for the exchange.
 
-Decomposition (first stage): the path shards by *output rows*.
-Every rank holds the cloud and builds the (cheap) geometry — octree, neighbour
-tables, dual cells — identically; the heavy stages are split by contiguous
-ranges of output voxels per grid level (the grids are Morton-ordered, so a range
-is a spatially compact set of cells):
+Decomposition: the path shards by *space*.  Every rank holds the cloud and
+builds the (cheap) geometry — octree, neighbour tables, dual cells — identically; the heavy
+stages are split by contiguous ranges of output voxels per grid level (the grids are Morton
+ordered, so a range is a spatially compact set of cells):
 
     aggregation search + continuous conv    level-0 voxel range
     every sparse convolution                output-row range of its table
     decoder MLP                             level-0 voxel range
 
-and after each stage the ranks exchange their rows with ONE all-gather
-(`all_gather_into_tensor`, in place in the full-size output buffer), so every
-rank again holds the whole feature tensor that the next gather-convolution
-reads.  Grids below `min_rows` rows are computed redundantly instead (no
-collective).  Results are identical to the single-GPU path row for row.  The one
-extra exchange forced by the reference's quirk 0 — the first V0
-entries of the *global* per-pair importance list — is an all-gather of the pair
-counts plus one all-reduce of a V0-float buffer.
+A stage writes only its own rows of the (full-size) feature tensor.  The next gather-convolution
+needs, besides its own rows, the *halo*: the rows its neighbour table references that another
+rank owns (one ring of face neighbours, a few percent of the rows).  Before each sharded
+convolution the ranks therefore exchange exactly those rows, peer to peer (grouped
+isend/irecv = ncclSend/ncclRecv over NVLink); the request lists are derived once per
+(neighbour table, input layout) from the table itself.  A full all-gather happens only where a
+sharded level feeds a replicated one (grids below `min_rows` rows are computed redundantly by
+every rank) and for the final [V0, 2] SDF values that contouring reads.  Results are identical to
+the single-GPU path row for row.  The one extra exchange forced by the reference's quirk 0
+ — the first V0 entries of the *global* per-pair importance list — is an all-reduce
+of the pair counts plus one all-reduce of a V0-float buffer.
 
-`ShardedOps(base, group)` wraps a kernel namespace (`asr_b200.ops` on GPUs; the
-CPU tests pass an oracle-backed namespace and the gloo backend) and is installed
-with `model.K = ShardedOps(...)`; model.py / pipeline.py are unchanged.
+`ShardedOps(base, group)` wraps a kernel namespace (`asr_b200.ops` on GPUs; the CPU tests pass
+an oracle-backed namespace and the gloo backend) and is installed with
+`model.K = ShardedOps(...)`; model.py / pipeline.py are unchanged.
 """
 import torch
 import torch.distributed as dist
@@ -46,6 +48,8 @@ class ShardedPlan:
         self.range = rng              # (a, b, n)
         self.entry_range = entry_range
         self.replicated = replicated
+        self.need = None              # sorted unique input rows this rank's share of the table reads
+        self.halo = {}                # input row count -> exchange lists (ShardedOps._halo_lists)
 
 
 class ShardedOps:
@@ -65,6 +69,13 @@ class ShardedOps:
         return getattr(self.base, name)
 
     # ------------------------------------------------------------------ helpers
+    # A tensor produced by a sharded stage carries `_asr_local = (a, b, n, padded buffer)`: only
+    # rows [a, b) (+ whatever halo was fetched into it) are valid.  No attribute = valid everywhere.
+    @staticmethod
+    def _tag(t, a, b, n, full):
+        t._asr_local = (a, b, n, full)
+        return t
+
     def _gather_rows(self, full, num_rows, n):
         """in-place all-gather of the per-rank row blocks of `full` ([world*n, C])."""
         dist.all_gather_into_tensor(full, full[self.rank * n:(self.rank + 1) * n], group=self.group)
@@ -72,8 +83,98 @@ class ShardedOps:
         self.bytes_gathered += full.numel() * full.element_size()
         return full[:num_rows]
 
+    def _make_full(self, x):
+        """all rows valid (a sharded level feeding a replicated stage)."""
+        tag = getattr(x, "_asr_local", None)
+        if tag is None:
+            return x
+        a, b, n, full = tag
+        if full is None or full.shape[1:] != x.shape[1:]:
+            full = torch.empty((n * self.world,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+            full[a:b] = x[a:b]
+        return self._gather_rows(full, x.shape[0], n)
+
     def _sharded(self, num_rows):
         return self.world > 1 and num_rows >= self.min_rows
+
+    def _halo_lists(self, plan, num_in):
+        """Who sends which input rows to whom for `plan`, given that the input tensor of
+        `num_in` rows is owned in contiguous blocks of n_in = ceil(num_in / world) rows."""
+        lists = plan.halo.get(num_in)
+        if lists is not None:
+            return lists
+        ia, ib, n_in = row_range(num_in, self.rank, self.world)
+        if plan.need is None:
+            e0, e1 = plan.entry_range
+            plan.need = torch.unique(plan.idx[e0:e1].long())
+        remote = plan.need[(plan.need < ia) | (plan.need >= ib)]
+        owner = torch.div(remote, n_in, rounding_mode="floor")
+        want = torch.bincount(owner, minlength=self.world)[:self.world]  # rows I want from each rank
+        table = torch.empty((self.world, self.world), dtype=torch.int64, device=want.device)
+        dist.all_gather_into_tensor(table.reshape(-1), want.contiguous(), group=self.group)
+        want_l, give_l = want.tolist(), table[:, self.rank].tolist()  # give_l[r] = rows rank r wants from me
+        recv_idx = remote  # ascending, hence grouped by owner
+        send_idx = torch.empty(int(sum(give_l)), dtype=torch.int64, device=want.device)
+        ops, o_r, o_s = [], 0, 0
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            if want_l[r]:
+                ops.append(dist.P2POp(dist.isend, recv_idx[o_r:o_r + want_l[r]].contiguous(), r, self.group))
+            if give_l[r]:
+                ops.append(dist.P2POp(dist.irecv, send_idx[o_s:o_s + give_l[r]], r, self.group))
+            o_r += want_l[r]
+            o_s += give_l[r]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        lists = (send_idx, give_l, recv_idx, want_l)
+        plan.halo[num_in] = lists
+        self.collectives += 1
+        return lists
+
+    def _fetch_halo(self, plan, x):
+        """make the rows of `x` that this rank's share of `plan` reads valid (in place)."""
+        tag = getattr(x, "_asr_local", None)
+        if tag is None:
+            return x
+        send_idx, give_l, recv_idx, want_l = self._halo_lists(plan, x.shape[0])
+        send = x.index_select(0, send_idx)
+        recv = torch.empty((recv_idx.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        ops, o_r, o_s = [], 0, 0
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            if give_l[r]:
+                ops.append(dist.P2POp(dist.isend, send[o_s:o_s + give_l[r]], r, self.group))
+            if want_l[r]:
+                ops.append(dist.P2POp(dist.irecv, recv[o_r:o_r + want_l[r]], r, self.group))
+            o_r += want_l[r]
+            o_s += give_l[r]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            x.index_copy_(0, recv_idx, recv)
+            self.collectives += 1
+            self.bytes_gathered += recv.numel() * recv.element_size()
+        return x
+
+    # concatenation / residual add of the U-Net (model.py) keep the validity tag
+    def cat(self, tensors, dim=-1):
+        out = torch.cat(tensors, dim)
+        tags = [getattr(t, "_asr_local", None) for t in tensors]
+        tag = next((t for t in tags if t is not None), None)
+        if tag is not None:
+            assert all(t is None or t[:3] == tag[:3] for t in tags)
+            self._tag(out, tag[0], tag[1], tag[2], None)
+        return out
+
+    def add(self, x, y):
+        out = x + y
+        tag = getattr(x, "_asr_local", None) or getattr(y, "_asr_local", None)
+        if tag is not None:
+            self._tag(out, tag[0], tag[1], tag[2], None)
+        return out
 
     # ------------------------------------------------------------------ sparse convolution
     def ConvPlan(self, neighbors_index, neighbors_kernel_index, neighbors_row_splits, kernel_size):
@@ -92,6 +193,7 @@ class ShardedOps:
                     importance_col=0, normalize=False, normalize_col=0, normalizer=None, bias=None, relu=False,
                     **kw):
         if plan.replicated:
+            inp_features = self._make_full(inp_features)
             return self.base.sparse_conv(plan.base, filters, inp_features, inp_importance=inp_importance,
                                          neighbors_importance=neighbors_importance, importance_col=importance_col,
                                          normalize=normalize, normalize_col=normalize_col, normalizer=normalizer,
@@ -99,6 +201,7 @@ class ShardedOps:
         a, b, n = plan.range
         e0, e1 = plan.entry_range
         cout = filters.shape[2]
+        inp_features = self._fetch_halo(plan, inp_features)
         full = torch.empty((n * self.world, cout), dtype=torch.float32, device=inp_features.device)
         local = full[self.rank * n:self.rank * n + (b - a)]
         self.base.sparse_conv(plan.base, filters, inp_features, inp_importance=inp_importance,
@@ -106,7 +209,7 @@ class ShardedOps:
                               importance_col=importance_col, normalize=normalize, normalize_col=normalize_col,
                               normalizer=None if normalizer is None else normalizer[a:b].contiguous(), bias=bias,
                               relu=relu, out=local, **kw)
-        return self._gather_rows(full, plan.num_out, n)
+        return self._tag(full[:plan.num_out], a, b, n, full)
 
     # ------------------------------------------------------------------ aggregation
     def multi_radius_search(self, points, queries, radii, frame=None):
@@ -138,7 +241,7 @@ class ShardedOps:
         self.base.continuous_conv(filters, out_positions[a:b].contiguous(), extents[a:b].contiguous(), offset,
                                   inp_positions, inp_features, inp_importance, neighbors_index, neighbors_importance,
                                   neighbors_row_splits, normalize=normalize, bias=bias, relu=relu, out=local)
-        return self._gather_rows(full, V, n)
+        return self._tag(full[:V], a, b, n, full)
 
     def pair_importance_for_unet(self, importance, num_voxels):
         """First `num_voxels` entries of the GLOBAL pair-importance list (the only ones
@@ -165,6 +268,7 @@ class ShardedOps:
     def decode(self, shifts, code, *weights, signed_scale=None, with_gradient=False):
         V = code.shape[0]
         if with_gradient or not self._sharded(V):
+            code = self._make_full(code)
             return self.base.decode(shifts, code, *weights, signed_scale=signed_scale, with_gradient=with_gradient)
         a, b, n = row_range(V, self.rank, self.world)
         full = torch.empty((n * self.world, 2), dtype=torch.float32, device=code.device)

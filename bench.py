@@ -42,6 +42,17 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def conv_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the sparse-conv tile kernel, from the
+    committed ncu capture of this workload (profiles/, latest round); None if there is none."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_sparse_conv_tc_traffic.json")))
+    if not files:
+        return None
+    with open(files[-1]) as f:
+        return json.load(f).get("traffic_bytes_per_launch")
+
+
 def workload_name(args):
     return "%s %.3gM pts, %d grid levels, full v0 U-Net (seeded random weights), fp32" % (
         args.workload, args.points / 1e6, args.levels)
@@ -187,8 +198,8 @@ def run_gpu(args):
     _lib.set_option("sparse_conv_output_stationary", args.conv_os)
     peaks = load_peaks()
 
-    # N > 1: ONE cloud, the path sharded by output-voxel ranges across the ranks with an all-gather
-    # of the produced rows after every sharded stage (asr_b200/shard.py) -> strong scaling
+    # N > 1: ONE cloud, the path sharded by output-voxel ranges across the ranks with a halo-row
+    # exchange before every sharded convolution (asr_b200/shard.py) -> strong scaling
     cloud = clouds.make(args.workload, args.points, seed=args.seed)
     net = model.seeded_weights(model.UNet(args.levels), seed=0).cuda()
     if world > 1:
@@ -294,7 +305,7 @@ def run_gpu(args):
         roofline = {
             "bound": "tensor", "kernel": "sparse_conv_tc_kernel" if ops.SPARSE_CONV_BACKEND == "tensor" else "sparse_conv_tile_kernel",
             "achieved": achieved, "peak": peak,
-            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": conv_traffic_per_launch(),
             "peak_source": "%s bf16 dense, sustained (kernel timed inside a long step)" % peaks["source"],
             "note": ("tcgen05.mma kind::tf32 with a 3xTF32 split: 3 tensor-pipe flops per algorithmic flop, and tf32 runs "
                      "at half the bf16 rate, so 1/6 of the bf16 peak is this scheme's ceiling" if ops.SPARSE_CONV_BACKEND == "tensor"
@@ -322,7 +333,8 @@ def run_gpu(args):
             "vs_baseline": None, "dtype": "f32 (3xTF32 on tcgen05 for the sparse convs)" if ops.SPARSE_CONV_BACKEND == "tensor" else "f32",
             "data": "synthetic",
             "config": {"workload": workload_name(args), "sparse_conv_backend": ops.SPARSE_CONV_BACKEND, "parallelism": ("%d gpus: geometry replicated, search/conv/decode sharded by output-voxel ranges, "
-                                       "all-gather of output rows per sharded stage (%d collectives, %.2f GB gathered per step)"
+                                       "peer-to-peer halo-row exchange before each sharded conv (%d exchanges, %.3f GB "
+                                       "received per rank and step)"
                                        % (world, net.K.collectives // max(total_steps, 1),
                                           net.K.bytes_gathered / max(total_steps, 1) / 1e9)) if world > 1 else "1 gpu",
                        "l2_policy": "inputs and every intermediate tensor larger than the 126 MB L2",

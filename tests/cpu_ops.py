@@ -65,6 +65,14 @@ def sparse_conv(plan, filters, x, inp_importance=None, neighbors_importance=None
     return res
 
 
+def cat(tensors, dim=-1):
+    return torch.cat(tensors, dim)
+
+
+def add(x, y):
+    return x + y
+
+
 def reduce_subarrays_sum(values, row_splits, index=None):
     v = values if index is None else values[index.long()]
     return ops_cpu.reduce_subarrays_sum(v, row_splits)
