@@ -36,10 +36,11 @@ class StageTimer:
 
 
 def build_input_dict(points, normals, radii, bb_min, bb_max, levels=5, radius_scale=1.0, max_depth=21, timer=None,
-                     K=ops):
+                     K=ops, normals_ready=None):
     """Grid building + aggregation search (asr.cpp:143-312).  Returns
     (input_dict, dual_vertex_indices, octree).  K = kernel namespace (ops or
-    shard.ShardedOps: there the aggregation arrays cover this rank's voxels)."""
+    shard.ShardedOps: there the aggregation arrays cover this rank's voxels).
+    normals_ready: CUDA event after which `normals` (copied on another stream) may be read."""
     timer = timer or StageTimer()
     timer.start()
     tree = K.Octree(points, radii, bb_min, bb_max, radius_scale, 0, max_depth)
@@ -49,6 +50,8 @@ def build_input_dict(points, normals, radii, bb_min, bb_max, levels=5, radius_sc
     grids = tree.grids(levels, True)
     timer.lap("grids")
     ones = torch.ones((points.shape[0], 1), dtype=torch.float32, device=points.device)
+    if normals_ready is not None:
+        torch.cuda.current_stream().wait_event(normals_ready)
     d = {"points": points, "feats": torch.cat([normals, ones], 1)}
     for i, g in enumerate(grids):
         for k, v in g.items():
@@ -81,7 +84,8 @@ def run_network(model, input_dict, timer=None):
 
 
 def reconstruct_vertices(model, points, normals, radii, bb_min=None, bb_max=None, levels=None, radius_scale=1.0,
-                         max_depth=21, contouring_value_threshold=1.0, timer=None, triangles=False):
+                         max_depth=21, contouring_value_threshold=1.0, timer=None, triangles=False,
+                         normals_ready=None):
     """Whole path on device tensors.  bb defaults to the exact min/max of the
     points like the C++ driver (asr.cpp:148-150).  triangles=True also runs the polygon
     passes of CreateTriangleMesh: the result then has "triangles"
@@ -92,7 +96,8 @@ def reconstruct_vertices(model, points, normals, radii, bb_min=None, bb_max=None
         bb_min = points.min(0).values.cpu().numpy()
         bb_max = points.max(0).values.cpu().numpy()
     K = getattr(model, "K", ops)
-    d, duals, tree = build_input_dict(points, normals, radii, bb_min, bb_max, levels, radius_scale, max_depth, timer, K)
+    d, duals, tree = build_input_dict(points, normals, radii, bb_min, bb_max, levels, radius_scale, max_depth, timer, K,
+                                      normals_ready)
     values = run_network(model, d, timer)
     timer.start()
     tris = None
@@ -123,20 +128,47 @@ def _to_host(t, key):
     return view
 
 
-def reconstruct_vertices_host(model, points, normals, radii, bb_min=None, bb_max=None, **kw):
-    """Same path with HOST (numpy) buffers in and out: H2D of the cloud, the
-    device path, D2H of the vertices and SDF values.  This is the call the
-    `e2e` benchmark number times."""
+_COPY_STREAM = None
+
+
+def _as_host_tensor(a):
+    """numpy array or CPU tensor -> contiguous float32 CPU tensor (pinned memory is used as is)."""
+    if isinstance(a, torch.Tensor):
+        return a.contiguous() if a.dtype == torch.float32 else a.float().contiguous()
+    return torch.from_numpy(np.ascontiguousarray(a, np.float32))
+
+
+def reconstruct_vertices_host(model, points, normals, radii, bb_min=None, bb_max=None, pinned_out=False, **kw):
+    """Same path with HOST buffers in and out (numpy arrays or CPU tensors, ideally pinned): H2D of
+    the cloud, the device path, D2H of the vertices and SDF values.  This is the call the `e2e`
+    benchmark number times.  The normals (first needed by the aggregation, after the octree and the
+    grids are built) are copied on a second stream, behind the geometry stages.
+    pinned_out=True returns views of the cached pinned staging buffers instead of fresh numpy copies."""
+    global _COPY_STREAM
     dev = torch.device("cuda")
-    p = torch.from_numpy(np.ascontiguousarray(points, np.float32)).to(dev, non_blocking=True)
-    n = torch.from_numpy(np.ascontiguousarray(normals, np.float32)).to(dev, non_blocking=True)
-    r = torch.from_numpy(np.ascontiguousarray(radii, np.float32)).to(dev, non_blocking=True)
+    hp, hn, hr = _as_host_tensor(points), _as_host_tensor(normals), _as_host_tensor(radii)
     if bb_min is None:
-        bb_min, bb_max = points.min(0), points.max(0)
-    out = reconstruct_vertices(model, p, n, r, bb_min, bb_max, **kw)
+        bb_min, bb_max = hp.min(0).values.numpy(), hp.max(0).values.numpy()
+    main = torch.cuda.current_stream()
+    if _COPY_STREAM is None:
+        _COPY_STREAM = torch.cuda.Stream()
+    p = hp.to(dev, non_blocking=True)
+    r = hr.to(dev, non_blocking=True)
+    _COPY_STREAM.wait_stream(main)
+    with torch.cuda.stream(_COPY_STREAM):
+        n = hn.to(dev, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(_COPY_STREAM)
+    n.record_stream(main)
+    out = reconstruct_vertices(model, p, n, r, bb_min, bb_max, normals_ready=ready, **kw)
     v, s = _to_host(out["vertices"], "vertices"), _to_host(out["values"], "values")
     t = _to_host(out["triangles"], "triangles") if "triangles" in out else None
-    torch.cuda.current_stream().synchronize()
+    main.synchronize()
+    if pinned_out:
+        res = {"vertices": v, "values": s}
+        if t is not None:
+            res["triangles"] = t
+        return res
     res = {"vertices": v.numpy().copy(), "values": s.numpy().copy()}
     if t is not None:
         res["triangles"] = t.numpy().copy()

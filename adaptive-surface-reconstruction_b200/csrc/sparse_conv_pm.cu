@@ -396,8 +396,11 @@ sparse_conv_pm_kernel(PmArgs a) {
     } else if (lane == 0) {
         // ================================================================ MMA issuer + filter loader
         const long long tm0 = a.dbg ? clock64() : 0;
-        const uint32_t idesc = umma::make_idesc_tf32(128, nc);
+        const uint32_t idesc = umma::make_idesc_tf32(128, nc), idesc2 = umma::make_idesc_tf32(128, 2 * nc);
         const int chunks_total = (a.Cin + KC - 1) / KC;
+        const uint64_t d_raw0 = umma::desc_base(kA_LBO, kA_SBO) + (umma::smem_u32(sRaw) >> 4);
+        const uint64_t d_lo0 = umma::desc_base(kA_LBO, kA_SBO) + (umma::smem_u32(sLo) >> 4);
+        const uint64_t d_b0 = umma::desc_base(kB_LBO, kB_SBO) + (umma::smem_u32(sB) >> 4);
         int cur_slot = -1, cur_p = -1;
         uint32_t b_phase = 0;
         int r = 0, q = 0, qph = 0;
@@ -446,17 +449,15 @@ sparse_conv_pm_kernel(PmArgs a) {
                 // fence.proxy.async lies on the causality path loader -> converter -> this thread
                 umma::tc_fence_after();
                 PM_T0();
-                const uint32_t a_hi = umma::smem_u32(sRaw + (size_t)r * kATileBytes);
-                const uint32_t a_lo = umma::smem_u32(sLo + (size_t)q * kATileBytes);
-                const uint32_t b_hi = umma::smem_u32(sB + (size_t)c * b_chunk_bytes), b_lo = b_hi + b_chunk_bytes / 2;
+                const uint64_t a_hi0 = d_raw0 + (uint64_t)(r * (int)(kATileBytes >> 4));
+                const uint64_t a_lo0 = d_lo0 + (uint64_t)(q * (int)(kATileBytes >> 4));
+                const uint64_t b_hi0 = d_b0 + (uint64_t)(c * (int)(b_chunk_bytes >> 4));
 #pragma unroll
                 for (int ks = 0; ks < KC / 8; ++ks) {
-                    const uint32_t oa = ks * 2 * kA_LBO, ob = ks * 2 * kB_LBO;
-                    const uint64_t dah = make_desc(a_hi + oa, kA_LBO, kA_SBO), dal = make_desc(a_lo + oa, kA_LBO, kA_SBO);
-                    const uint64_t dbh = make_desc(b_hi + ob, kB_LBO, kB_SBO), dbl = make_desc(b_lo + ob, kB_LBO, kB_SBO);
-                    umma::mma_tf32(t_main, dah, dbh, idesc, c > 0 || ks > 0);
-                    umma::mma_tf32(t_corr, dal, dbh, idesc, c > 0 || ks > 0);
-                    umma::mma_tf32(t_corr, dah, dbl, idesc, true);
+                    const uint64_t oa = (uint64_t)(ks * 2 * (kA_LBO >> 4)), ob = (uint64_t)(ks * 2 * (kB_LBO >> 4));
+                    // A_hi x [B_hi | B_lo] -> (main | correction) in one MMA of width 2 nc (sparse_conv_tc.cu)
+                    umma::mma_tf32(t_main, a_hi0 + oa, b_hi0 + ob, idesc2, c > 0 || ks > 0);
+                    umma::mma_tf32_acc(t_corr, a_lo0 + oa, b_hi0 + ob, idesc);
                 }
                 umma::mma_commit(&raw_empty[r]);
                 umma::mma_commit(&lo_empty[q]);

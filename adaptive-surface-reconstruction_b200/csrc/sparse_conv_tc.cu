@@ -224,28 +224,36 @@ sparse_conv_tc_kernel(TcArgs a) {
         umma::bulk_wait_read();  // the staging rows live in this CTA's shared memory
     } else if ((tid & 31) == 0) {
         // ------------------------------------------------------------ MMA issuer
-        const uint32_t idesc = umma::make_idesc_tf32(128, NT);
+        const uint32_t idesc = umma::make_idesc_tf32(128, NT), idesc2 = umma::make_idesc_tf32(128, 2 * NT);
         const int groups = (MT == 2 && count > TM) ? 2 : 1;  // a half-empty tile skips its second group
+        // descriptors = constant part + (address >> 4): a few adds per MMA instead of re-assembly
+        const uint64_t da0 = umma::desc_base(kA_LBO, kA_SBO) + (umma::smem_u32(smem) >> 4);
+        const uint64_t db0 = umma::desc_base(kB_LBO, kB_SBO) + (umma::smem_u32(smem) >> 4);
+        const uint32_t st16 = stage_bytes >> 4, a_tile16 = kATileBytes >> 4;
+        int st = 0, ph = 0;
         for (int c = 0; c < chunks; ++c) {
-            const int st = c % S, use = c / S;
-            umma::mbar_wait(&mbar_full[st], use & 1);
+            umma::mbar_wait(&mbar_full[st], ph);
             umma::tc_fence_after();
-            const uint32_t s_base = umma::smem_u32(smem + st * stage_bytes);
-            const uint32_t b_hi = s_base + MT * 2 * kATileBytes, b_lo = b_hi + b_bytes;
+            const uint64_t a_st = da0 + (uint64_t)(st * st16);
+            const uint64_t b_hi0 = db0 + (uint64_t)(st * st16 + MT * 2 * a_tile16);
             for (int g = 0; g < groups; ++g) {
-                const uint32_t a_hi = s_base + g * 2 * kATileBytes, a_lo = a_hi + kATileBytes;
+                const uint64_t a_hi0 = a_st + (uint64_t)(g * 2 * a_tile16), a_lo0 = a_hi0 + a_tile16;
                 const uint32_t t_main = tmem + g * 2 * NT, t_corr = t_main + NT;
 #pragma unroll
                 for (int ks = 0; ks < KC / 8; ++ks) {
-                    const uint32_t oa = ks * 2 * kA_LBO, ob = ks * 2 * kB_LBO;
-                    const uint64_t dah = make_desc(a_hi + oa, kA_LBO, kA_SBO), dal = make_desc(a_lo + oa, kA_LBO, kA_SBO);
-                    const uint64_t dbh = make_desc(b_hi + ob, kB_LBO, kB_SBO), dbl = make_desc(b_lo + ob, kB_LBO, kB_SBO);
-                    umma::mma_tf32(t_main, dah, dbh, idesc, c > 0 || ks > 0);
-                    umma::mma_tf32(t_corr, dal, dbh, idesc, c > 0 || ks > 0);
-                    umma::mma_tf32(t_corr, dah, dbl, idesc, true);
+                    const uint64_t oa = (uint64_t)(ks * 2 * (kA_LBO >> 4)), ob = (uint64_t)(ks * 2 * (kB_LBO >> 4));
+                    // A_hi x [B_hi | B_lo]: the lo rows follow the hi rows in the stage and the correction
+                    // accumulator follows the main one in TMEM, so main and A_hi B_lo are ONE MMA of
+                    // width 2 NT (fewer, longer tensor-core instructions; A_hi is read once)
+                    umma::mma_tf32(t_main, a_hi0 + oa, b_hi0 + ob, idesc2, c > 0 || ks > 0);
+                    umma::mma_tf32_acc(t_corr, a_lo0 + oa, b_hi0 + ob, idesc);
                 }
             }
             umma::mma_commit(&mbar_empty[st]);
+            if (++st == S) {
+                st = 0;
+                ph ^= 1;
+            }
         }
         umma::mma_commit(&mbar_acc);
     }

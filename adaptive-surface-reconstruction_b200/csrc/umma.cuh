@@ -120,6 +120,20 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
     d |= (uint64_t)1 << 46;
     return d;
 }
+// The descriptor's address field is (addr >> 4) in the low 14 bits and shared-memory addresses
+// stay below 256 KB, so descriptors of tiles with the same strides differ by a plain add:
+// desc(addr) = desc_base(lbo, sbo) + (addr >> 4).  The MMA-issuing thread runs alone on its
+// scheduler (no latency hiding), so its per-MMA instruction count IS the issue rate: build the
+// constant part once and add offsets in the loop instead of re-assembling descriptors.
+__device__ __forceinline__ uint64_t desc_base(uint32_t lbo, uint32_t sbo) {
+    return ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+// same as mma_tf32 with the accumulate flag already in a predicate-friendly register
+__device__ __forceinline__ void mma_tf32_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+                 "l"(adesc), "l"(bdesc), "r"(idesc)
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
     asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
 }

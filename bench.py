@@ -212,14 +212,10 @@ def run_gpu(args):
         return pipeline.reconstruct_vertices(net, devt["points"], devt["normals"], devt["radii"], bb[0], bb[1])
 
     def step_host():
-        p = host["points"].cuda(non_blocking=True)
-        n = host["normals"].cuda(non_blocking=True)
-        r = host["radii"].cuda(non_blocking=True)
-        out = pipeline.reconstruct_vertices(net, p, n, r, bb[0], bb[1])
-        v = pipeline._to_host(out["vertices"], "bench_vertices")
-        s = pipeline._to_host(out["values"], "bench_values")
-        torch.cuda.current_stream().synchronize()  # the step's results are on the host
-        return out, v, s
+        # the public host-buffer entry point: pinned H2D of the cloud, the path, D2H of vertices + values
+        res = pipeline.reconstruct_vertices_host(net, host["points"], host["normals"], host["radii"], bb[0], bb[1],
+                                                 pinned_out=True)
+        return None, res["vertices"], res["values"]
 
     def barrier():
         if world > 1:
