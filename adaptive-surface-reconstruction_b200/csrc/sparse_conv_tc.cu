@@ -288,6 +288,8 @@ pack_conv_filters_kernel(const float* __restrict__ W, int K, int Cin, int Cout, 
 // tuning knobs (asr_set_option): pipeline depth for n_pad <= 128 and row groups per CTA
 static int g_tc_stages = 2;
 static int g_tc_mt = 1;
+static int g_tc_ntile = 128;  // output columns per CTA (dev knob: 64 trades a second gather for more CTAs per SM)
+void sparse_conv_tc_ntile(int n) { g_tc_ntile = n >= 128 ? 128 : (n >= 64 ? 64 : 32); }
 void sparse_conv_tc_tune(int stages, int mt) {
     if (stages > 0) g_tc_stages = std::min(stages, kMaxStages);
     if (mt > 0) g_tc_mt = mt >= 2 ? 2 : 1;
@@ -318,7 +320,8 @@ void sparse_conv_tc_tiles(const ConvPlan& P, const float* x, const float* wp, in
     a.p_in = P.p_in.get();
     a.p_out = P.p_out.get();
     a.perm = P.perm.get();
-    a.n_tile = std::min(n_pad, 128);
+    a.n_tile = std::min(n_pad, g_tc_ntile);
+    while (n_pad % a.n_tile) a.n_tile /= 2;
     const int MT = (g_tc_mt == 2 && P.has_tiles2) ? 2 : 1;
     a.tiles = (const int4*)(MT == 2 ? P.tiles2.get() : P.tiles.get());
     a.num_tiles = MT == 2 ? P.num_tiles2.get() : P.num_tiles.get();
