@@ -7,9 +7,8 @@ reference, the work happens on the current CUDA device.
 
 In scope (hot path): create_octree, create_grids_from_octree,
 create_dual_vertex_indices, reconstruct_surface (octree-conv -> SDF -> vertices).
-The "next" rows f-1 (triangle connectivity) and f-3 (remove_connected_components) are built
-on the GPU as well; f-2 (KDTree: radius estimation / density pre-filter) is not built yet and
-raises NotImplementedError instead of silently running elsewhere.
+The "next" rows f-1 (triangle connectivity), f-2 (KDTree: radius estimation, outlier and
+density pre-filters) and f-3 (remove_connected_components) run on the GPU as well.
 """
 import os
 import warnings
@@ -110,8 +109,10 @@ def reconstruct_surface(points, normals, radii, point_radius_scale=1.0, density_
     (asr.cpp:95-349).  Runs the hot path (grid building, aggregation search,
     aggregate/unet/decode, dual-contouring vertices) on the GPU.
 
-    Not built yet: the kNN radius estimation / density pre-filter
-    (radii must be given; density_percentile_threshold is ignored).
+    Pre-filter as in asr.cpp:114-138: without radii they are estimated from the
+    `point_radius_estimation_knn` nearest neighbours and outliers are dropped; with radii the
+    sparsest `density_percentile_threshold` percent of the points are dropped (see
+    asr_b200.ops.density_inlier for the one deliberate difference to the reference).
     `model` (an asr_b200.model.UNet) overrides the model.pt lookup."""
     points = _f32(points, "points", "points must have shape [num_points,3]", 2, 3)
     normals = np.ascontiguousarray(normals, dtype=np.float32)
@@ -122,15 +123,25 @@ def reconstruct_surface(points, normals, radii, point_radius_scale=1.0, density_
         raise ValueError("radii must have shape [num_point3]")
     if points.shape[0] == 0:
         raise RuntimeError("points is null!\n")
-    if radii.size == 0:
-        raise NotImplementedError("radius estimation (KDTree.compute_k_radius, SURVEY.md §8f-2) is not built yet: "
-                                  "pass per-point radii")
-    net = model if model is not None else _load_model()
+    # preprocessing (asr.cpp:114-138): estimate the radii from the k nearest neighbours and drop
+    # outliers, or, with given radii, drop the sparsest points
     dev = torch.device("cuda")
     p = torch.from_numpy(points).to(dev)
-    out = _pipeline.reconstruct_vertices(net, p, torch.from_numpy(normals).to(dev), torch.from_numpy(radii).to(dev),
-                                         points.min(0), points.max(0), radius_scale=float(point_radius_scale),
-                                         max_depth=int(octree_max_depth),
+    tree = _ops.KDTree(p)
+    if radii.size == 0:
+        r = tree.compute_k_radius(int(point_radius_estimation_knn))
+        keep = tree.compute_inlier(r, 0.5, int(point_radius_estimation_knn), 1)
+    else:
+        r = torch.from_numpy(radii).to(dev)
+        keep = _ops.density_inlier(tree.compute_radius_neighbors(r), float(density_percentile_threshold))
+    del tree
+    p, r = p[keep].contiguous(), r[keep].contiguous()
+    nrm = torch.from_numpy(normals).to(dev)[keep].contiguous()
+    if p.shape[0] == 0:
+        raise RuntimeError("points is null!\n")
+    net = model if model is not None else _load_model()
+    out = _pipeline.reconstruct_vertices(net, p, nrm, r, p.min(0).values.cpu().numpy(), p.max(0).values.cpu().numpy(),
+                                         radius_scale=float(point_radius_scale), max_depth=int(octree_max_depth),
                                          contouring_value_threshold=float(contouring_value_threshold), triangles=True)
     # asr.cpp:343-345: RemoveConnectedComponents with the caller's limits
     v, t = _ops.remove_connected_components(out["vertices"], out["triangles"], int(keep_n_connected_components),
@@ -152,10 +163,30 @@ def remove_connected_components(vertices, triangles, keep_n_largest_components, 
 
 
 class KDTree:
-    """module.cpp:455-489 — pre-filter row f-2, outside the hot path."""
+    """module.cpp:455-489 (row f-2): nearest-neighbour statistics of a cloud, on the GPU."""
 
     def __init__(self, points):
-        points = np.asarray(points)
+        points = np.ascontiguousarray(points, dtype=np.float32)
         if points.ndim != 2 or points.shape[1] != 3:
             raise ValueError("points must have shape [N,3]")
-        raise NotImplementedError("KDTree (SURVEY.md §8f-2) is not built yet")
+        self._num = points.shape[0]
+        self._impl = _ops.KDTree(torch.from_numpy(points).cuda())
+
+    def compute_k_radius(self, k):
+        """module.cpp:459 / pyComputeKRadius: distance to the k-th nearest point (itself included)."""
+        return self._impl.compute_k_radius(int(k)).cpu().numpy()
+
+    def _radii(self, radii):
+        radii = np.ascontiguousarray(radii, dtype=np.float32)
+        if radii.ndim != 1 or radii.shape[0] != self._num:
+            raise ValueError("radii must have shape [N]")
+        return torch.from_numpy(radii).cuda()
+
+    def compute_inlier(self, radii, radius_fraction=0.5, k=24, outlier_threshold=1):
+        """module.cpp:468."""
+        return self._impl.compute_inlier(self._radii(radii), float(radius_fraction), int(k),
+                                         int(outlier_threshold)).cpu().numpy()
+
+    def compute_radius_neighbors(self, radii):
+        """module.cpp:483: number of points within each point's radius, as a list of ints."""
+        return self._impl.compute_radius_neighbors(self._radii(radii)).cpu().tolist()

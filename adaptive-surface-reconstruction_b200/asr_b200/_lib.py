@@ -63,6 +63,10 @@ SIGNATURES = {
     "asr_contour_triangles_fill": (_i32, [_vp, _vp, _vp, _vp]),
     "asr_contour_triangles_destroy": (None, [_vp]),
     "asr_mesh_components": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp]),
+    "asr_kdtree_create": (_i32, [_vp, _i64, _vp, _pp]),
+    "asr_kdtree_k_radius": (_i32, [_vp, _i32, _vp, _vp]),
+    "asr_kdtree_inlier": (_i32, [_vp, _vp, _f32, _i32, _i32, _vp, _vp]),
+    "asr_radius_neighbor_counts": (_i32, [_vp, _i64, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -492,3 +492,62 @@ def remove_connected_components(vertices, triangles, keep_n_largest_components, 
     tl = tris.long()
     tmask = mask[tl[:, 0]] & mask[tl[:, 1]] & mask[tl[:, 2]]
     return vertices[mask].contiguous(), new_index[tl[tmask]].to(torch.int32).contiguous()
+
+
+# ------------------------------------------------------------------------------------ point pre-processing (f-2)
+
+
+class KDTree:
+    """Nearest-neighbour queries of a cloud among itself (reference KDTree, nsearch.cpp:22-105)."""
+
+    def __init__(self, points):
+        self.points = _cuda(points, torch.float32, "points")
+        if self.points.ndim != 2 or self.points.shape[1] != 3:
+            raise ValueError("points must have shape [N,3]")
+        self._h = C.c_void_p(0)
+        check(lib().asr_kdtree_create(_ptr(self.points), self.points.shape[0], _stream(), C.byref(self._h)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().asr_radius_search_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def compute_k_radius(self, k):
+        out = torch.empty(self.points.shape[0], dtype=torch.float32, device=self.points.device)
+        check(lib().asr_kdtree_k_radius(self._h, int(k), _ptr(out), _stream()))
+        return out
+
+    def compute_inlier(self, radii, radius_fraction=0.5, k=24, outlier_threshold=1):
+        radii = _cuda(radii, torch.float32, "radii")
+        if radii.shape != (self.points.shape[0],):
+            raise ValueError("radii must have shape [N]")
+        out = torch.empty(self.points.shape[0], dtype=torch.uint8, device=self.points.device)
+        check(lib().asr_kdtree_inlier(self._h, _ptr(radii), float(radius_fraction), int(k), int(outlier_threshold),
+                                      _ptr(out), _stream()))
+        return out.bool()
+
+    def compute_radius_neighbors(self, radii):
+        radii = _cuda(radii, torch.float32, "radii")
+        if radii.shape != (self.points.shape[0],):
+            raise ValueError("radii must have shape [N]")
+        out = torch.empty(self.points.shape[0], dtype=torch.int32, device=self.points.device)
+        check(lib().asr_radius_neighbor_counts(_ptr(self.points), self.points.shape[0], _ptr(radii), _ptr(out),
+                                               _stream()))
+        return out
+
+
+def density_inlier(radius_neighbors, density_percentile_threshold):
+    """Points whose radius-neighbour count exceeds the count at the percentile rank
+    (ComputeInlierFromDensity, preprocess.cpp:38-62).  NOTE: the reference compares the
+    *partially sorted* count array with the threshold (:50-61), so which points it keeps depends on
+    std::partial_sort's unspecified remainder order; this keeps the documented intent — the same
+    NUMBER of points, selected by their own count."""
+    n = radius_neighbors.shape[0]
+    middle = int((float(density_percentile_threshold) / 100.0) * n)
+    middle = min(n, max(1, middle))
+    threshold = torch.kthvalue(radius_neighbors.to(torch.int64), middle).values
+    return radius_neighbors > threshold

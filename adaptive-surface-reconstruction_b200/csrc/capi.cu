@@ -237,6 +237,33 @@ int asr_radius_search_fill(asr_search* search, int32_t* idx, float* dist, int64_
 }
 void asr_radius_search_destroy(asr_search* search) { delete search; }
 
+int asr_kdtree_create(const float* d_points, int64_t num_points, void* stream, asr_search** out) {
+    return guarded([&] {
+        ASRB_REQUIRE(out, "null argument");
+        ASRB_REQUIRE(num_points >= 0 && num_points < (int64_t(1) << 31), "bad point count");
+        auto h = std::make_unique<asr_search>();
+        knn_build(h->s, d_points, num_points, S(stream));
+        *out = h.release();
+    });
+}
+int asr_kdtree_k_radius(asr_search* tree, int k, float* d_out, void* stream) {
+    return guarded([&] {
+        ASRB_REQUIRE(tree, "null handle");
+        knn_radius(tree->s, k, d_out, S(stream));
+    });
+}
+int asr_kdtree_inlier(asr_search* tree, const float* d_radii, float radius_fraction, int k, int outlier_threshold,
+                      uint8_t* d_out, void* stream) {
+    return guarded([&] {
+        ASRB_REQUIRE(tree, "null handle");
+        knn_inlier(tree->s, d_radii, radius_fraction, k, outlier_threshold, d_out, S(stream));
+    });
+}
+int asr_radius_neighbor_counts(const float* d_points, int64_t num_points, const float* d_radii, int32_t* d_out,
+                               void* stream) {
+    return guarded([&] { radius_neighbor_counts(d_points, num_points, d_radii, d_out, S(stream)); });
+}
+
 int asr_scale_compatibility(const float* sizes, const float* radii, const int32_t* idx, const int64_t* splits,
                             int64_t num_queries, float* out, void* stream) {
     return guarded([&] { scale_compat(sizes, radii, idx, splits, num_queries, out, S(stream)); });

@@ -436,4 +436,217 @@ void scale_compat(const float* d_sizes, const float* d_radii, const int32_t* d_i
     ASRB_CHECK_LAUNCH();
 }
 
+
+
+// =====================================================================================
+// k-nearest-neighbour queries of the points among themselves — SURVEY.md §8 row f-2.
+//
+// Replaces KDTree::ComputeKRadius / ComputeInlier / ComputeRadiusNeighbors (reference
+// cpp/lib/nsearch.cpp:30-105; nanoflann KD-tree + TBB).  Same Morton-sorted point array as the
+// radius search; one warp owns a query point:
+//   1. the 62 sorted neighbours of the point are loaded once and give, for every power-of-two
+//      cell size, how many points share the point's cell -> the smallest cell size whose own
+//      cell already holds k points is the starting scale;
+//   2. the 3 x 3 x 3 block of cells around the point is streamed (windows by binary search in
+//      the sorted codes), squared distances in nanoflann's operation order, and the k smallest
+//      are kept as a sorted list spread over the lanes (insertion by ballot + shuffle);
+//   3. the k-th distance is exact once it does not exceed the distance to the block's boundary
+//      (>= one cell); otherwise the cell size doubles and the block is rescanned.
+// k <= 32 (the reference's default is 24).
+namespace {
+
+__device__ __forceinline__ long long lower_bound_code(const Key* __restrict__ a, long long n, Key k) {
+    long long lo = 0, hi = n;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (__ldg(a + mid) < k) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+template <bool INLIER>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+knn_kernel(const Key* __restrict__ codes, const float4* __restrict__ spts, long long n, int k, float cell0,
+           float* __restrict__ out_radius, const float* __restrict__ radii, float fraction, int vote_limit,
+           uint8_t* __restrict__ out_inlier) {
+    __shared__ unsigned s_begin[kWarpsPerBlock][32];
+    __shared__ int s_pre[kWarpsPerBlock][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long i = blockIdx.x * (long long)kWarpsPerBlock + warp;
+    if (i >= n) return;
+    const float4 q = __ldg(spts + i);
+    const Key code = __ldg(codes + i);
+    // 1. starting scale
+    const long long li = i - 1 - lane, ri = i + 1 + lane;
+    const Key L = li >= 0 ? __ldg(codes + li) : ~Key(0), R = ri < n ? __ldg(codes + ri) : ~Key(0);
+    int sh = 0;
+    for (; sh < kGridBits; ++sh) {
+        const Key pref = code >> (3 * sh);
+        const unsigned ml = __ballot_sync(0xffffffffu, li >= 0 && (L >> (3 * sh)) == pref);
+        const unsigned mr = __ballot_sync(0xffffffffu, ri < n && (R >> (3 * sh)) == pref);
+        const int run = 1 + (__ffs(~ml) - 1 < 0 ? 32 : __ffs(~ml) - 1) + (__ffs(~mr) - 1 < 0 ? 32 : __ffs(~mr) - 1);
+        if (run >= k) break;
+    }
+    float best_d = __int_as_float(0x7f800000);  // sorted ascending over the lanes
+    int best_i = -1;
+    for (;;) {
+        // 2. windows of the 27 cells around the point at this scale
+        const int cells_per_axis = 1 << (kGridBits - sh);
+        const Key cc = code >> (3 * sh);
+        const int cx = (int)compact3(cc), cy = (int)compact3(cc >> 1), cz = (int)compact3(cc >> 2);
+        unsigned begin = 0;
+        int len = 0;
+        if (lane < 27) {
+            const int x = cx + lane % 3 - 1, y = cy + (lane / 3) % 3 - 1, z = cz + lane / 9 - 1;
+            if (x >= 0 && y >= 0 && z >= 0 && x < cells_per_axis && y < cells_per_axis && z < cells_per_axis) {
+                const Key c = morton3(x, y, z);
+                const long long b = lower_bound_code(codes, n, c << (3 * sh));
+                const long long e = sh == kGridBits ? n : lower_bound_code(codes, n, (c + 1) << (3 * sh));
+                begin = (unsigned)b;
+                len = (int)(e - b);
+            }
+        }
+        int pre = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, pre, d);
+            if (lane >= d) pre += v;
+        }
+        s_begin[warp][lane] = begin;
+        s_pre[warp][lane + 1] = pre;
+        if (lane == 0) s_pre[warp][0] = 0;
+        __syncwarp();
+        const int total = __shfl_sync(0xffffffffu, pre, 31);
+        best_d = __int_as_float(0x7f800000);
+        best_i = -1;
+        for (int t0 = 0; t0 < total; t0 += 32) {
+            const int t = t0 + lane;
+            float d2 = __int_as_float(0x7f800000);
+            int pi = -1;
+            if (t < total) {
+                int c = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1)
+                    if (c + step < 32 && s_pre[warp][c + step] <= t) c += step;
+                const float4 p = __ldg(spts + s_begin[warp][c] + (unsigned)(t - s_pre[warp][c]));
+                const float dx = __fsub_rn(q.x, p.x), dy = __fsub_rn(q.y, p.y), dz = __fsub_rn(q.z, p.z);
+                d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                pi = __float_as_int(p.w);
+            }
+            const float kth = __shfl_sync(0xffffffffu, best_d, k - 1);
+            unsigned acc = __ballot_sync(0xffffffffu, d2 < kth);
+            while (acc) {
+                const int src = __ffs(acc) - 1;
+                acc &= acc - 1;
+                const float c = __shfl_sync(0xffffffffu, d2, src);
+                const int ci = __shfl_sync(0xffffffffu, pi, src);
+                // later candidates of the batch may have fallen behind the updated k-th value
+                if (!(c < __shfl_sync(0xffffffffu, best_d, k - 1))) continue;
+                const int pos = __popc(__ballot_sync(0xffffffffu, best_d <= c));
+                const float up_d = __shfl_up_sync(0xffffffffu, best_d, 1);
+                const int up_i = __shfl_up_sync(0xffffffffu, best_i, 1);
+                if (lane > pos) {
+                    best_d = up_d;
+                    best_i = up_i;
+                } else if (lane == pos) {
+                    best_d = c;
+                    best_i = ci;
+                }
+            }
+        }
+        __syncwarp();
+        // 3. exact once the k-th distance lies inside the scanned block
+        const float kth = __shfl_sync(0xffffffffu, best_d, k - 1);
+        const float cover = cell0 * (float)(1 << sh) * 0.9999f;
+        if (sh >= kGridBits || kth <= cover * cover) break;
+        ++sh;
+    }
+    const int valid = __popc(__ballot_sync(0xffffffffu, best_i >= 0 && lane < k));
+    const long long self = __float_as_int(q.w);
+    if (!INLIER) {
+        const float dmax = valid > 0 ? __shfl_sync(0xffffffffu, best_d, max(valid, 1) - 1) : 0.f;
+        if (lane == 0) out_radius[self] = sqrtf(dmax);
+    } else {
+        const float limit = __fmul_rn(radii[self], fraction);
+        const bool vote = lane < valid && radii[best_i] < limit;
+        const int votes = __popc(__ballot_sync(0xffffffffu, vote));
+        if (lane == 0) out_inlier[self] = votes < vote_limit ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+row_counts_kernel(const int64_t* __restrict__ splits, long long n, int32_t* __restrict__ out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int32_t)(splits[i + 1] - splits[i]);
+}
+}  // namespace
+
+void knn_build(Search& S, const float* d_points, int64_t n, cudaStream_t s) {
+    // the sorted point array of the radius search, binned over the points' bounding cube
+    S.n = n;
+    S.nq = 0;
+    DevBuf<unsigned> mm(6, s);
+    ASRB_CUDA(cudaMemsetAsync(mm.get(), 0xff, 3 * sizeof(unsigned), s));
+    ASRB_CUDA(cudaMemsetAsync(mm.get() + 3, 0, 3 * sizeof(unsigned), s));
+    unsigned h[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0, 0, 0};
+    if (n > 0) {
+        const unsigned blocks = (unsigned)std::min<size_t>(grid_for(n, 256), 148 * 8);
+        bbox_kernel<<<blocks, 256, 0, s>>>(d_points, n, mm.get(), mm.get() + 3);
+        ASRB_CHECK_LAUNCH();
+        ASRB_CUDA(cudaMemcpyAsync(h, mm.get(), sizeof(h), cudaMemcpyDeviceToHost, s));
+        ASRB_CUDA(cudaStreamSynchronize(s));
+    }
+    float edge = 0.f;
+    for (int a = 0; a < 3; ++a) {
+        const float lo = h[a] == 0xffffffffu ? 0.f : from_ordered_bits(h[a]);
+        const float hi = h[3 + a] == 0 ? 0.f : from_ordered_bits(h[3 + a]);
+        S.frame_origin[a] = lo;
+        edge = std::max(edge, hi - lo);
+    }
+    if (!(edge > 0.f)) edge = 1.f;
+    S.frame_inv_h = (float)(2097152.0 / ((double)edge * 1.000001));
+    BinFrame f{{S.frame_origin[0], S.frame_origin[1], S.frame_origin[2]}, S.frame_inv_h};
+    S.codes.alloc((size_t)n, s);
+    S.spts.alloc((size_t)n, s);
+    DevBuf<uint32_t> order((size_t)n, s);
+    if (n > 0) {
+        ProfileScope prof("knn_point_sort", s);
+        point_code_kernel<<<grid_for(n, 256), 256, 0, s>>>(d_points, n, f, S.codes.get(), order.get());
+        ASRB_CHECK_LAUNCH();
+        sort_pairs_u64_u32(S.codes.get(), order.get(), (size_t)n, s, 63);
+        gather_points_kernel<<<grid_for(n, 256), 256, 0, s>>>(d_points, order.get(), n, (float4*)S.spts.get());
+        ASRB_CHECK_LAUNCH();
+    }
+}
+
+void knn_radius(const Search& S, int k, float* d_out, cudaStream_t s) {
+    ASRB_REQUIRE(k >= 1 && k <= 32, "k must be in [1, 32]");
+    if (S.n == 0) return;
+    ProfileScope prof("knn_radius", s);
+    knn_kernel<false><<<grid_for(S.n, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
+            S.codes.get(), (const float4*)S.spts.get(), S.n, k, 1.0f / S.frame_inv_h, d_out, nullptr, 0.f, 0, nullptr);
+    ASRB_CHECK_LAUNCH();
+}
+
+void knn_inlier(const Search& S, const float* d_radii, float fraction, int k, int outlier_threshold, uint8_t* d_out,
+                cudaStream_t s) {
+    ASRB_REQUIRE(k >= 1 && k <= 32, "k must be in [1, 32]");
+    if (S.n == 0) return;
+    ProfileScope prof("knn_inlier", s);
+    knn_kernel<true><<<grid_for(S.n, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
+            S.codes.get(), (const float4*)S.spts.get(), S.n, k, 1.0f / S.frame_inv_h, nullptr, d_radii, fraction,
+            outlier_threshold, d_out);
+    ASRB_CHECK_LAUNCH();
+}
+
+// number of points with |p - p_i|^2 < r_i^2 for every point (ComputeRadiusNeighbors, nsearch.cpp:87-105)
+void radius_neighbor_counts(const float* d_points, int64_t n, const float* d_radii, int32_t* d_out, cudaStream_t s) {
+    if (n == 0) return;
+    Search S;
+    search_prepare(S, d_points, n, d_points, d_radii, n, nullptr, s);
+    row_counts_kernel<<<grid_for(n, 256), 256, 0, s>>>(S.splits.get(), n, d_out);
+    ASRB_CHECK_LAUNCH();
+}
+
 }  // namespace asrb

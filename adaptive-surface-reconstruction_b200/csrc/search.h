@@ -26,4 +26,11 @@ void search_fill(Search& S, int32_t* d_idx, float* d_d2, int64_t* d_splits, cuda
 void scale_compat(const float* d_sizes, const float* d_radii, const int32_t* d_idx, const int64_t* d_splits,
                   int64_t nq, float* d_out, cudaStream_t s);
 
+// kNN over the points themselves (reference KDTree, nsearch.cpp:30-105); S holds the sorted points
+void knn_build(Search& S, const float* d_points, int64_t n, cudaStream_t s);
+void knn_radius(const Search& S, int k, float* d_out, cudaStream_t s);
+void knn_inlier(const Search& S, const float* d_radii, float fraction, int k, int outlier_threshold, uint8_t* d_out,
+                cudaStream_t s);
+void radius_neighbor_counts(const float* d_points, int64_t n, const float* d_radii, int32_t* d_out, cudaStream_t s);
+
 }  // namespace asrb

@@ -215,6 +215,20 @@ int asr_contour_triangles_create(const float* d_values, const int64_t* d_dual_in
 int asr_contour_triangles_fill(void* handle, float* d_vertices, int32_t* d_triangles, void* stream);
 void asr_contour_triangles_destroy(void* handle);
 
+/* ---------------------------------------------------------------- point pre-processing (row f-2)
+ * replaces asr::KDTree (cpp/lib/nsearch.cpp:22-105; python KDTree, module.cpp:455-489).
+ * _k_radius: sqrt of the largest of the k smallest squared distances, the point itself included
+ * (ComputeKRadius :30-52); _inlier: 1 unless at least `outlier_threshold` of the k nearest points
+ * have a radius < radius_fraction * own radius (ComputeInlier :54-85); counts: number of points
+ * with |p - p_i|^2 < r_i^2 (ComputeRadiusNeighbors :87-105).  k <= 32.  The handle is destroyed
+ * with asr_radius_search_destroy. */
+int asr_kdtree_create(const float* d_points, int64_t num_points, void* stream, asr_search** out);
+int asr_kdtree_k_radius(asr_search* tree, int k, float* d_out, void* stream);
+int asr_kdtree_inlier(asr_search* tree, const float* d_radii, float radius_fraction, int k, int outlier_threshold,
+                      uint8_t* d_out, void* stream);
+int asr_radius_neighbor_counts(const float* d_points, int64_t num_points, const float* d_radii, int32_t* d_out,
+                               void* stream);
+
 /* ---------------------------------------------------------------- mesh post-processing
  * replaces asr::ConnectedComponents (cpp/lib/postprocess.cpp:81-141), the core of
  * RemoveConnectedComponents (:143-176; python remove_connected_components, module.cpp:348).

@@ -197,3 +197,52 @@ def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_
         nz = norm != 0
         out[nz] = out[nz] / norm[nz][:, None]
     return out
+
+
+# ---------------------------------------------------------------- point pre-processing (row f-2)
+def _f32_d2(q, p):
+    """nanoflann L2_Simple_Adaptor for dim 3 in float32: ((dx*dx) + dy*dy) + dz*dz."""
+    d = (q.astype(np.float32) - p.astype(np.float32)).astype(np.float32)
+    return ((d[..., 0] * d[..., 0]).astype(np.float32) + (d[..., 1] * d[..., 1]).astype(np.float32)).astype(
+        np.float32) + (d[..., 2] * d[..., 2]).astype(np.float32)
+
+
+def knn(points, k, extra=8):
+    """(sorted float32 squared distances [N, k], indices [N, k]) of the k nearest points (the point
+    itself included), reference KDTree::ComputeKRadius / ComputeInlier (nsearch.cpp:30-85).  The
+    candidates come from a float64 cKDTree query of k + extra neighbours, the ranking is redone
+    with nanoflann's float32 arithmetic."""
+    from scipy.spatial import cKDTree
+    points = np.ascontiguousarray(points, np.float32)
+    kk = min(points.shape[0], k + extra)
+    _, idx = cKDTree(points.astype(np.float64)).query(points.astype(np.float64), k=kk, workers=-1)
+    idx = idx.reshape(points.shape[0], kk)
+    d2 = _f32_d2(points[:, None, :], points[idx])
+    order = np.argsort(d2, axis=1, kind="stable")[:, :min(k, kk)]
+    return np.take_along_axis(d2, order, 1), np.take_along_axis(idx, order, 1)
+
+
+def k_radius(points, k):
+    d2, _ = knn(points, k)
+    return np.sqrt(d2.max(1)).astype(np.float32)
+
+
+def knn_inlier(points, radii, radius_fraction=0.5, k=24, outlier_threshold=1):
+    _, idx = knn(points, k)
+    radii = np.asarray(radii, np.float32)
+    votes = (radii[idx] < (radii * np.float32(radius_fraction)).astype(np.float32)[:, None]).sum(1)
+    return votes < outlier_threshold
+
+
+def radius_neighbor_counts(points, radii):
+    """number of points with d2 < r^2 in float32 (ComputeRadiusNeighbors, nsearch.cpp:87-105)."""
+    from scipy.spatial import cKDTree
+    points = np.ascontiguousarray(points, np.float32)
+    radii = np.asarray(radii, np.float32)
+    tree = cKDTree(points.astype(np.float64))
+    out = np.zeros(points.shape[0], np.int32)
+    cand = tree.query_ball_point(points.astype(np.float64), radii.astype(np.float64) * 1.001 + 1e-12, workers=-1)
+    for i, c in enumerate(cand):
+        c = np.asarray(c, np.int64)
+        out[i] = int((_f32_d2(points[i][None, :], points[c]) < np.float32(radii[i]) * np.float32(radii[i])).sum())
+    return out

@@ -189,3 +189,38 @@ def test_remove_connected_components_matches_reference():
         v, t = ops.remove_connected_components(dev(verts), dev(tris), keep, mins)
         assert np.array_equal(v.cpu().numpy(), ref["vertices"]), (keep, mins)
         assert np.array_equal(t.cpu().numpy(), ref["triangles"]), (keep, mins)
+
+
+def test_kdtree_matches_float32_knn_oracle():
+    """Row f-2: k-radius, outlier flags and radius-neighbour counts against the float32
+    restatement of the nanoflann queries (oracle/ops_cpu.py)."""
+    import adaptivesurfacereconstruction as asr
+    from asr_b200 import clouds
+    from oracle import ops_cpu
+    for name, c in (("blob", clouds.adaptive_blob(20000, seed=5)), ("sphere", clouds.sphere(6000, seed=1))):
+        pts = c["points"]
+        tree = asr.KDTree(pts)
+        for k in (24, 1, 32, 7):
+            r = tree.compute_k_radius(k)
+            assert r.dtype == np.float32 and np.array_equal(r, ops_cpu.k_radius(pts, k)), (name, k)
+        r24 = tree.compute_k_radius(24)
+        rad = (r24 * np.random.default_rng(0).uniform(0.3, 2.0, len(r24))).astype(np.float32)
+        got = tree.compute_inlier(rad, 0.5, 24, 1)
+        ref = ops_cpu.knn_inlier(pts, rad, 0.5, 24, 1)
+        assert got.dtype == np.bool_ and (got != ref).mean() < 1e-3  # ties at the k-th distance pick either point
+        assert 0.0 < ref.mean() < 1.0
+        got3 = tree.compute_inlier(rad, 0.7, 16, 3)
+        assert (got3 != ops_cpu.knn_inlier(pts, rad, 0.7, 16, 3)).mean() < 1e-3
+        cnt = tree.compute_radius_neighbors(r24)
+        assert isinstance(cnt, list) and np.array_equal(np.asarray(cnt, np.int32), ops_cpu.radius_neighbor_counts(pts, r24))
+    with pytest.raises(ValueError):
+        asr.KDTree(np.zeros((5, 2), np.float32))
+
+
+def test_reconstruct_surface_estimates_radii():
+    import adaptivesurfacereconstruction as asr
+    from asr_b200 import clouds, model
+    c = clouds.sphere(6000, seed=2)
+    net = model.seeded_weights(model.UNet(5), seed=4).cuda()
+    mesh = asr.reconstruct_surface(c["points"], c["normals"], None, model=net, contouring_value_threshold=1e9)
+    assert set(mesh) == {"vertices", "triangles"} and mesh["triangles"].shape[1] == 3
