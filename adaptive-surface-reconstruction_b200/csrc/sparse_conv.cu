@@ -438,7 +438,19 @@ void sparse_conv_forward(const ConvPlan& P, const float* x, const float* w, cons
     ASRB_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0, "sparse_conv: channel counts must be multiples of 4");
     if (P.V_out == 0) return;
     if (wp && !imp_in && !imp_entry && !normalize && sparse_conv_os_supported(P, Cin, Cout)) {
-        sparse_conv_os(P, x, wp, Cin, Cout, bias, relu, out, s);
+        // common slots output-stationary (writes every row once); the sparse slots, if any, are
+        // reduced into that by the pair-major kernel before the bias / ReLU pass
+        const bool has_rare = P.rare && P.rare->E > 0;
+        sparse_conv_os(P, x, wp, Cin, Cout, has_rare ? nullptr : bias, has_rare ? 0 : relu, out, s);
+        if (has_rare) {
+            sparse_conv_tc_tiles(*P.rare, x, wp, Cin, Cout, nullptr, nullptr, Cout, out, s);
+            if (bias || relu) {
+                ProfileScope prof("sparse_conv_epilogue", s);
+                conv_epilogue_kernel<<<grid_for((size_t)P.V_out * (Cout / 4), 256), 256, 0, s>>>(
+                        out, P.V_out, Cout, 0, 0, nullptr, splits, bias, relu);
+                ASRB_CHECK_LAUNCH();
+            }
+        }
         return;
     }
     {

@@ -30,10 +30,11 @@ struct ConvPlan {
     // output-stationary form (sparse_conv_os.cu): per super-tile of 256 output rows the slots
     // that occur ("steps") and per step the gather index of every row (-1 = absent)
     bool os_ok = false;
-    int64_t os_steps = 0, os_tiles = 0;
+    int64_t os_steps = 0, os_tiles = 0, os_pairs = 0;  // os_pairs = entries of the output-stationary slots
     DevBuf<int64_t> os_off;   // [os_tiles + 1]
     DevBuf<int32_t> os_meta;  // [os_steps] slot | row-tile flags << 8
     DevBuf<int32_t> os_idx;   // [os_steps][256]
+    std::unique_ptr<ConvPlan> rare;  // entries of the slots that are not accumulated output-stationary
 };
 
 void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, const int64_t* d_splits, int64_t V_out,

@@ -1,8 +1,12 @@
 // Output-stationary persistent tensor-core sparse convolution.
 //
-// Used for the convolutions without importance weighting (conv2..4 of every block
-// and the decoder blocks) whose filter slice fits the shared-memory ring
-// (Cin <= 128, Cout <= 128).  The pair-major kernels (sparse_conv_pm.cu,
+// Used (option sparse_conv_output_stationary) for the convolutions without importance weighting
+// (conv2..4 of every block and the decoder blocks) whose filter slice fits the shared-memory ring
+// (Cin <= 128, Cout <= 128).  HYBRID form: only the kOsSlots "common" kernel slots (self + the 6
+// same-level faces: ~73 % of all pairs, each ~80 % dense) are accumulated output-stationary; the
+// sparse finer / coarser slots (the union of ALL slots over 256 rows is ~37 of 55 on adaptive
+// clouds, 4.5x the minimal MMA work) stay pair-major and are reduced into the written output by
+// the per-tile kernel, followed by the bias / ReLU pass.  The pair-major kernels (sparse_conv_pm.cu,
 // sparse_conv_tc.cu) add every 128-pair tile to the output with L2 reductions, and
 // measurements on B200 show those reductions — through red.global or through
 // cp.reduce.async.bulk alike — to saturate near 2 TB/s, which bounds the small-channel
@@ -48,6 +52,7 @@ constexpr int KC = umma::kKC;
 constexpr int kMaxRaw = 12;
 constexpr int kMaxLo = 3;
 constexpr int kMaxB = 16;
+constexpr int kOsSlots = 7;             // slots < kOsSlots are accumulated in TMEM, the rest pair-major
 constexpr int kEpiWarps = 4;
 constexpr int kCvtWarps = 8;
 constexpr int kLoadWarps = 2;
@@ -62,7 +67,7 @@ constexpr int kThreads = (kBWarp + 1) * 32;  // 512
 // ------------------------------------------------------------------ plan
 // pass 1: per super-tile the slot masks of its two row tiles
 __global__ void __launch_bounds__(ST)
-os_mask_kernel(const uint8_t* __restrict__ slot, const int64_t* __restrict__ splits, long long V,
+os_mask_kernel(const uint8_t* __restrict__ slot, const int64_t* __restrict__ splits, long long V, int limit,
                unsigned long long* __restrict__ mask01, int32_t* __restrict__ count, int* __restrict__ dup) {
     __shared__ unsigned long long s_m[ST / 32];
     const long long v = blockIdx.x * (long long)ST + threadIdx.x;
@@ -70,6 +75,7 @@ os_mask_kernel(const uint8_t* __restrict__ slot, const int64_t* __restrict__ spl
     if (v < V) {
         const int64_t e = splits[v + 1];
         for (int64_t j = splits[v]; j < e; ++j) {
+            if (slot[j] >= limit) continue;
             const unsigned long long b = 1ULL << slot[j];
             if (m & b) *dup = 1;  // a slot twice in one row: not expressible here, stay pair-major
             m |= b;
@@ -92,7 +98,7 @@ os_mask_kernel(const uint8_t* __restrict__ slot, const int64_t* __restrict__ spl
 // pass 2: step metadata (slot | tile flags << 8) and the per-row gather indices
 __global__ void __launch_bounds__(ST)
 os_fill_kernel(const int32_t* __restrict__ idx, const uint8_t* __restrict__ slot, const int64_t* __restrict__ splits,
-               long long V, const unsigned long long* __restrict__ mask01, const int64_t* __restrict__ off,
+               long long V, int limit, const unsigned long long* __restrict__ mask01, const int64_t* __restrict__ off,
                int32_t* __restrict__ meta, int32_t* __restrict__ sidx) {
     const long long v = blockIdx.x * (long long)ST + threadIdx.x;
     const unsigned long long m0 = mask01[2 * blockIdx.x], m1 = mask01[2 * blockIdx.x + 1], m = m0 | m1;
@@ -106,10 +112,38 @@ os_fill_kernel(const int32_t* __restrict__ idx, const uint8_t* __restrict__ slot
         const int64_t e = splits[v + 1];
         for (int64_t j = splits[v]; j < e; ++j) {
             const int k = slot[j];
+            if (k >= limit) continue;
             const int rank = __popcll(m & ((1ULL << k) - 1));
             sidx[(o + rank) * ST + threadIdx.x] = idx[j];
         }
     }
+}
+
+// the entries with slot >= limit as their own CSR (same rows), for the pair-major kernel
+__global__ void __launch_bounds__(256)
+os_rare_count_kernel(const uint8_t* __restrict__ slot, const int64_t* __restrict__ splits, long long V, int limit,
+                     int32_t* __restrict__ count) {
+    const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    int c = 0;
+    const int64_t e = splits[v + 1];
+    for (int64_t j = splits[v]; j < e; ++j) c += slot[j] >= limit ? 1 : 0;
+    count[v] = c;
+}
+__global__ void __launch_bounds__(256)
+os_rare_fill_kernel(const int32_t* __restrict__ idx, const uint8_t* __restrict__ slot, const int64_t* __restrict__ splits,
+                    long long V, int limit, const int64_t* __restrict__ rsplits, int32_t* __restrict__ ridx,
+                    uint8_t* __restrict__ rslot) {
+    const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    int64_t o = rsplits[v];
+    const int64_t e = splits[v + 1];
+    for (int64_t j = splits[v]; j < e; ++j)
+        if (slot[j] >= limit) {
+            ridx[o] = idx[j];
+            rslot[o] = slot[j];
+            ++o;
+        }
 }
 
 void os_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, const int64_t* d_splits, int64_t V_out,
@@ -121,7 +155,8 @@ void os_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, con
     DevBuf<int32_t> count((size_t)NU, s);
     DevBuf<int> dup(1, s);
     ASRB_CUDA(cudaMemsetAsync(dup.get(), 0, sizeof(int), s));
-    os_mask_kernel<<<(unsigned)NU, ST, 0, s>>>(d_slot, d_splits, V_out, mask01.get(), count.get(), dup.get());
+    const int limit = kOsSlots;
+    os_mask_kernel<<<(unsigned)NU, ST, 0, s>>>(d_slot, d_splits, V_out, limit, mask01.get(), count.get(), dup.get());
     ASRB_CHECK_LAUNCH();
     P.os_off.alloc((size_t)NU + 1, s);
     exclusive_sum_i32_to_i64(count.get(), P.os_off.get(), (size_t)NU, s);
@@ -132,9 +167,27 @@ void os_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, con
     P.os_meta.alloc((size_t)NS, s);
     P.os_idx.alloc((size_t)NS * ST, s);
     ASRB_CUDA(cudaMemsetAsync(P.os_idx.get(), 0xff, (size_t)NS * ST * sizeof(int32_t), s));
-    os_fill_kernel<<<(unsigned)NU, ST, 0, s>>>(d_idx, d_slot, d_splits, V_out, mask01.get(), P.os_off.get(),
+    os_fill_kernel<<<(unsigned)NU, ST, 0, s>>>(d_idx, d_slot, d_splits, V_out, limit, mask01.get(), P.os_off.get(),
                                                P.os_meta.get(), P.os_idx.get());
     ASRB_CHECK_LAUNCH();
+    // the remaining (finer / coarser) entries: their own pair-major plan
+    DevBuf<int32_t> rcount((size_t)V_out, s);
+    DevBuf<int64_t> rsplits((size_t)V_out + 1, s);
+    os_rare_count_kernel<<<grid_for(V_out, 256), 256, 0, s>>>(d_slot, d_splits, V_out, limit, rcount.get());
+    ASRB_CHECK_LAUNCH();
+    exclusive_sum_i32_to_i64(rcount.get(), rsplits.get(), (size_t)V_out, s);
+    const int64_t E_rare = d2h_scalar(rsplits.get() + V_out, s);
+    P.rare.reset();
+    P.os_pairs = P.E - E_rare;
+    if (E_rare > 0) {
+        DevBuf<int32_t> ridx((size_t)E_rare, s);
+        DevBuf<uint8_t> rslot((size_t)E_rare, s);
+        os_rare_fill_kernel<<<grid_for(V_out, 256), 256, 0, s>>>(d_idx, d_slot, d_splits, V_out, limit, rsplits.get(),
+                                                                 ridx.get(), rslot.get());
+        ASRB_CHECK_LAUNCH();
+        P.rare = std::make_unique<ConvPlan>();
+        conv_plan_build(*P.rare, ridx.get(), rslot.get(), rsplits.get(), V_out, E_rare, K, s, false);
+    }
     P.os_ok = true;
 }
 
@@ -411,51 +464,56 @@ sparse_conv_os_kernel(OsArgs a) {
             OS_FLUSH(1);
         }
     } else if (warp == kMmaWarp) {
-        // ================================================================ MMA issuer (lane 0; the warp loops together)
-        const uint32_t idesc = umma::make_idesc_tf32(128, nc), idesc2 = umma::make_idesc_tf32(128, 2 * nc);
-        const uint64_t d_raw0 = umma::desc_base(kA_LBO, kA_SBO) + (umma::smem_u32(sRaw) >> 4);
-        const uint64_t d_lo0 = umma::desc_base(kA_LBO, kA_SBO) + (umma::smem_u32(sLo) >> 4);
-        const uint64_t d_b0 = umma::desc_base(kB_LBO, kB_SBO) + (umma::smem_u32(sB) >> 4);
-        int r = 0, q = 0, qph = 0, bi = 0, n = 0;
-        for (long long u = u0; u < a.NU; u += du, ++n) {
-            long long j0;
-            const StepList L = load_steps(a, u, lane, j0);
-            const int ub = n % UB, use = n / UB;
-            if (use > 0) {
-                OS_T0();
-                mbar_wait(&acc_empty[ub], (use - 1) & 1);
-                OS_ACC(8);
-            }
-            umma::tc_fence_after();
-            dbg_w[15] += 1;
-            dbg_w[14] += L.n;
-            bool started[2] = {false, false};
-            for (int i = 0; i < L.n; ++i, bi += nch) {
-                const int flags = (L.get(i) >> 8) & 3;
-                const int last_t = (flags & 2) ? 1 : 0;
-                bool first_tile = true;
-                for (int t = 0; t < 2; ++t) {
-                    if (!((flags >> t) & 1)) continue;
-                    const uint32_t t_main = tmem + (uint32_t)(ub * 2 + t) * 2 * nc, t_corr = t_main + nc;
-                    for (int c = 0; c < nch; ++c) {
-                        const int bs = (bi + c) % NBS;
-                        if (first_tile) {
-                            OS_T0();
-                            mbar_wait(&b_full[bs], ((bi + c) / NBS) & 1);
-                            OS_ACC(6);
-                        }
-                        {
-                            OS_T0();
-                            mbar_wait(&lo_full[q], qph);
-                            OS_ACC(7);
-                        }
-                        dbg_w[13] += 1;
-                        umma::tc_fence_after();
-                        if (lane == 0) {
+        // ================================================================ MMA issuer (one thread: every extra
+        // instruction on its path costs issue rate; the step words are read
+        // straight from global memory, one step ahead)
+        if (lane == 0) {
+            const uint32_t idesc = umma::make_idesc_tf32(128, nc), idesc2 = umma::make_idesc_tf32(128, 2 * nc);
+            const uint64_t d_raw0 = umma::desc_base(kA_LBO, kA_SBO) + (umma::smem_u32(sRaw) >> 4);
+            const uint64_t d_lo0 = umma::desc_base(kA_LBO, kA_SBO) + (umma::smem_u32(sLo) >> 4);
+            const uint64_t d_b0 = umma::desc_base(kB_LBO, kB_SBO) + (umma::smem_u32(sB) >> 4);
+            int r = 0, q = 0, qph = 0, bi = 0, n = 0;
+            for (long long u = u0; u < a.NU; u += du, ++n) {
+                const long long j0 = __ldg(a.os_off + u);
+                const int nsteps = (int)(__ldg(a.os_off + u + 1) - j0);
+                const int ub = n % UB, use = n / UB;
+                if (use > 0) {
+                    OS_T0();
+                    mbar_wait(&acc_empty[ub], (use - 1) & 1);
+                    OS_ACC(8);
+                }
+                umma::tc_fence_after();
+                dbg_w[15] += 1;
+                dbg_w[14] += nsteps;
+                bool started0 = false, started1 = false;
+                int meta_next = nsteps > 0 ? __ldg(a.os_meta + j0) : 0;
+                for (int i = 0; i < nsteps; ++i, bi += nch) {
+                    const int flags = (meta_next >> 8) & 3;
+                    if (i + 1 < nsteps) meta_next = __ldg(a.os_meta + j0 + i + 1);
+                    const int last_t = (flags & 2) ? 1 : 0;
+                    bool first_tile = true;
+                    for (int t = 0; t < 2; ++t) {
+                        if (!((flags >> t) & 1)) continue;
+                        const uint32_t t_main = tmem + (uint32_t)(ub * 2 + t) * 2 * nc, t_corr = t_main + nc;
+                        const bool started = t ? started1 : started0;
+                        for (int c = 0; c < nch; ++c) {
+                            const int bs = (bi + c) % NBS;
+                            if (first_tile) {
+                                OS_T0();
+                                mbar_wait(&b_full[bs], ((bi + c) / NBS) & 1);
+                                OS_ACC(6);
+                            }
+                            {
+                                OS_T0();
+                                mbar_wait(&lo_full[q], qph);
+                                OS_ACC(7);
+                            }
+                            dbg_w[13] += 1;
+                            umma::tc_fence_after();
                             const uint64_t a_hi0 = d_raw0 + (uint64_t)(r * (int)(kATileBytes >> 4));
                             const uint64_t a_lo0 = d_lo0 + (uint64_t)(q * (int)(kATileBytes >> 4));
                             const uint64_t b_hi0 = d_b0 + (uint64_t)(bs * (int)(b_chunk_bytes >> 4));
-                            const bool acc0 = started[t] || c > 0;
+                            const bool acc0 = started || c > 0;
 #pragma unroll
                             for (int ks = 0; ks < KC / 8; ++ks) {
                                 const uint64_t oa = (uint64_t)(ks * 2 * (kA_LBO >> 4)), ob = (uint64_t)(ks * 2 * (kB_LBO >> 4));
@@ -466,29 +524,28 @@ sparse_conv_os_kernel(OsArgs a) {
                             umma::mma_commit(&raw_empty[r]);
                             umma::mma_commit(&lo_empty[q]);
                             if (t == last_t) umma::mma_commit(&b_empty[bs]);
+                            if (++r == R) r = 0;
+                            if (++q == Q) {
+                                q = 0;
+                                qph ^= 1;
+                            }
                         }
-                        __syncwarp();
-                        if (++r == R) r = 0;
-                        if (++q == Q) {
-                            q = 0;
-                            qph ^= 1;
-                        }
+                        if (t) started1 = true;
+                        else started0 = true;
+                        first_tile = false;
                     }
-                    started[t] = true;
-                    first_tile = false;
                 }
+                umma::mma_commit(&acc_full[ub]);
             }
-            if (lane == 0) umma::mma_commit(&acc_full[ub]);
-            __syncwarp();
-        }
-        if (a.dbg && blockIdx.x == 0 && lane == 0) {
-            g_os_dbg[5] += (unsigned long long)(clock64() - t_role0);
-            OS_FLUSH(6);
-            OS_FLUSH(7);
-            OS_FLUSH(8);
-            OS_FLUSH(13);
-            OS_FLUSH(14);
-            OS_FLUSH(15);
+            if (a.dbg && blockIdx.x == 0) {
+                g_os_dbg[5] += (unsigned long long)(clock64() - t_role0);
+                OS_FLUSH(6);
+                OS_FLUSH(7);
+                OS_FLUSH(8);
+                OS_FLUSH(13);
+                OS_FLUSH(14);
+                OS_FLUSH(15);
+            }
         }
     } else {
         // ================================================================ filter loader (lane 0; the warp loops together)
@@ -584,8 +641,8 @@ void sparse_conv_os(const ConvPlan& P, const float* x, const float* wp, int Cin,
     }
     ASRB_CUDA(cudaFuncSetAttribute(sparse_conv_os_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     char label[96];
-    snprintf(label, sizeof(label), "sparse_conv_tile/os K%d %dx%d E%lld", P.K, Cin, Cout, (long long)P.E);
-    ProfileScope prof(label, s, 2.0 * (double)P.E * Cin * Cout);
+    snprintf(label, sizeof(label), "sparse_conv_tile/os K%d %dx%d E%lld", P.K, Cin, Cout, (long long)P.os_pairs);
+    ProfileScope prof(label, s, 2.0 * (double)P.os_pairs * Cin * Cout);
     const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(n_sm, P.os_tiles));
     a.dbg = g_os_debug == 1;
     if (a.dbg) {

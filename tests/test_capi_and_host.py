@@ -129,3 +129,41 @@ def test_clouds_are_deterministic_and_bench_byte_model():
                                           "importance": True}])
     assert by["sparse_conv_stack"] == 4 * 4 * 32 + 4 * 4 * 64 + 5 * 20 + 8 * 5 + 4 * 55 * 32 * 64 + 32
     assert by["search"] == 12 * 10 + 16 * 4 + 12 * 30 + 8 * 5
+
+
+def test_ply_reader_and_writer(tmp_path):
+    """Row f-4: the PLY flavours asrtool reads (cpp/bin/main.cpp:25-112) and the mesh it writes."""
+    from asr_b200 import plyio
+    rng = np.random.default_rng(0)
+    pts = rng.standard_normal((50, 3)).astype(np.float32)
+    nrm = rng.standard_normal((50, 3)).astype(np.float32)
+    rad = rng.uniform(0.1, 1, 50).astype(np.float32)
+    head = "ply\nformat %s 1.0\ncomment test\nelement vertex 50\n" + "".join(
+        "property float %s\n" % n for n in ("x", "y", "z", "nx", "ny", "nz")) + "%send_header\n"
+    # ascii with radii called `value`
+    a = tmp_path / "a.ply"
+    with open(a, "w") as f:
+        f.write(head % ("ascii", "property double value\n"))
+        for i in range(50):
+            f.write(" ".join(repr(float(v)) for v in (*pts[i], *nrm[i], rad[i])) + "\n")
+    p, n, r = plyio.read_points(str(a))
+    assert np.array_equal(p, pts) and np.array_equal(n, nrm) and np.array_equal(r, rad)
+    # binary little / big endian, no radii
+    for fmt, end in (("binary_little_endian", "<"), ("binary_big_endian", ">")):
+        b = tmp_path / (fmt + ".ply")
+        with open(b, "wb") as f:
+            f.write((head % (fmt, "")).encode())
+            f.write(np.concatenate([pts, nrm], 1).astype(end + "f4").tobytes())
+        p, n, r = plyio.read_points(str(b))
+        assert np.array_equal(p, pts) and np.array_equal(n, nrm) and r.size == 0
+    # normals missing -> empty result like ReadPoints
+    c = tmp_path / "c.ply"
+    with open(c, "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex 1\nproperty float x\nproperty float y\nproperty float z\n"
+                "end_header\n0 0 0\n")
+    assert plyio.read_points(str(c))[0].shape == (0, 3)
+    tri = np.array([[0, 1, 2], [2, 3, 4]], np.int32)
+    m = tmp_path / "m.ply"
+    plyio.write_mesh(str(m), pts, tri)
+    v, t = plyio.read_mesh(str(m))
+    assert np.array_equal(v, pts) and np.array_equal(t, tri)

@@ -122,3 +122,19 @@ def test_open3d_ops_called_like_the_reference():
                                       torch.zeros(3), pts.cpu(), feats.cpu(), torch.empty(0), idx.cpu(), nimp.cpu(),
                                       rs.cpu(), normalize=True, dtype=torch.float64)
     assert (y.cpu().double() - torch.relu(ref + conv.bias.cpu().double())).abs().max() <= 1e-4
+
+
+def test_asrtool_ply_to_ply(tmp_path):
+    """Row f-4: the command line tool end to end (seeded random weights: model.pt is not available offline)."""
+    from asr_b200 import asrtool, clouds, plyio
+    c = clouds.sphere(5000, seed=3)
+    src = tmp_path / "cloud.ply"
+    with open(src, "wb") as f:
+        f.write(("ply\nformat binary_little_endian 1.0\nelement vertex %d\n" % len(c["points"]) + "".join(
+            "property float %s\n" % n for n in ("x", "y", "z", "nx", "ny", "nz", "radius")) + "end_header\n").encode())
+        f.write(np.concatenate([c["points"], c["normals"], c["radii"][:, None]], 1).astype("<f4").tobytes())
+    dst = tmp_path / "mesh.ply"
+    assert asrtool.main(["--in", str(src), "--out", str(dst), "--random-weights", "4"]) == 0
+    v, t = plyio.read_mesh(str(dst))
+    assert v.shape[1] == 3 and t.shape[1] == 3 and (t.size == 0 or t.max() < len(v))
+    assert asrtool.main(["--version"]) == 0 and asrtool.main([]) == 1

@@ -30,6 +30,9 @@ def run(label, **opts):
           ", ".join("%s=%.1f" % (k.split("/")[1], m) for m, k in top)), flush=True)
 run("stages=2 mt=1", tc_stages=2, tc_row_groups=1)
 if len(sys.argv) > 2 and sys.argv[2] == "one": sys.exit(0)
+if len(sys.argv) > 2 and sys.argv[2] == "os":
+    run("hybrid os", sparse_conv_output_stationary=1)
+    sys.exit(0)
 if len(sys.argv) > 2 and sys.argv[2] == "ntile":
     run("ntile=64 stages=2", tc_ntile=64)
     run("ntile=64 stages=3", tc_ntile=64, tc_stages=3)
