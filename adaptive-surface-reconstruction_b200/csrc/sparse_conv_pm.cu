@@ -46,8 +46,8 @@ constexpr int TM = 128;
 constexpr int KC = umma::kKC;
 constexpr int kMaxRaw = 12;             // raw (= hi operand) ring
 constexpr int kMaxLo = 3;               // lo operand ring
-constexpr int kEpiWarps = 4;            // warps 0..3   (TMEM lane quarter = warp id)
-constexpr int kCvtWarps = 8;            // warps 4..11
+constexpr int kEpiWarps = 8;            // warps 0..7: TMEM lane quarter = warp & 3, column half = warp >> 2
+constexpr int kCvtWarps = 4;            // warps 8..11
 constexpr int kLoadWarps = 2;           // warps 12..13
 constexpr int kCvtThreads = kCvtWarps * 32;
 constexpr int kLoadThreads = kLoadWarps * 32;
@@ -199,8 +199,12 @@ sparse_conv_pm_kernel(PmArgs a) {
 
     if (warp < kEpiWarps) {
         // ================================================================ epilogue
-        const int row = tid;  // pair inside the tile = TMEM lane
-        float* T = reinterpret_cast<float*>(smem + a.off_t) + (size_t)row * (a.eb + 4);
+        // 8 warps: the accumulator read-out (not the MMAs) was the busiest role with 4.  A thread
+        // owns one pair (TMEM lane) and one half of the part's columns.
+        const int row = (warp & 3) * 32 + lane;  // pair inside the tile = TMEM lane
+        const int half = warp >> 2;
+        const int hc = nc >> 1;                  // columns per thread
+        float* T = reinterpret_cast<float*>(smem + a.off_t) + (size_t)tid * (a.eb + 4);
         auto meta = [&](const ItemIter& q, int& o, float& imp) {
             const int cnt = (int)min((long long)TM, q.len - (long long)q.t * TM);
             const long long s0 = q.base + (long long)q.t * TM;
@@ -220,34 +224,34 @@ sparse_conv_pm_kernel(PmArgs a) {
             const int buf = n & 1, use = n >> 1;
             const int o = o_next;
             const float imp = imp_next;
-            const int col0 = (it.p % a.nparts) * nc;
+            const int col0 = (it.p % a.nparts) * nc + half * hc;  // first column of this thread
             iter_next(a, it);
-            const int ncols_valid = min(nc, a.Cout - col0);
+            const int ncols_valid = min(hc, a.Cout - col0);
             {
                 PM_T0();
                 mbar_wait(&acc_full[buf], use & 1);
                 PM_ACC(7);
             }
             umma::tc_fence_after();
-            const uint32_t t_acc = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * 2 * nc;
-            for (int nb = 0; nb < nc; nb += a.eb) {
+            const uint32_t t_acc = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * 2 * nc + half * hc;
+            for (int nb = 0; nb < hc; nb += a.eb) {
                 {
                     PM_T0();
                     umma::bulk_wait_read();  // the staging row is free again
                     PM_ACC(8);
                 }
-                for (int n0 = 0; n0 < a.eb; n0 += 32) {
-                    uint32_t m[32], c[32];
+                for (int n0 = 0; n0 < a.eb; n0 += 16) {
+                    uint32_t m[16], c[16];
                     {
                         PM_T0();
-                        umma::tmem_ld32_issue(t_acc + nb + n0, m);
-                        umma::tmem_ld32_issue(t_acc + nc + nb + n0, c);
-                        umma::tmem_ld_wait32(m);
-                        umma::tmem_ld_wait32(c);
+                        umma::tmem_ld16_issue(t_acc + nb + n0, m);
+                        umma::tmem_ld16_issue(t_acc + nc + nb + n0, c);
+                        umma::tmem_ld_wait16(m);
+                        umma::tmem_ld_wait16(c);
                         PM_ACC(13);
                     }
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
+                    for (int j = 0; j < 16; j += 4) {
                         float e[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -257,7 +261,7 @@ sparse_conv_pm_kernel(PmArgs a) {
                         *reinterpret_cast<float4*>(T + n0 + j) = make_float4(e[0], e[1], e[2], e[3]);
                     }
                 }
-                if (nb + a.eb >= nc) {  // the accumulators are in registers / staged: release the TMEM buffer
+                if (nb + a.eb >= hc) {  // the accumulators are in registers / staged: release the TMEM buffer
                     umma::tc_fence_before();
                     mbar_arrive(&acc_empty[buf]);
                 }
@@ -287,10 +291,9 @@ sparse_conv_pm_kernel(PmArgs a) {
         // ================================================================ converters
         // raw tile (fp32 bits; the tensor core reads them as tf32 = hi, ignoring the 13 low
         // mantissa bits) -> lo = x - hi tile.  No global loads here, so the proxy fence is cheap.
-        const int ct = tid - kEpiWarps * 32;  // 0..255
-        const int kq = ct & 3, rsub = ct >> 2;
+        const int ct = tid - kEpiWarps * 32;  // 0..127
+        const int kq = ct & 3, rsub = ct >> 2;  // rows rsub + 32 j, j = 0..3
         const uint32_t off0 = (uint32_t)(rsub >> 3) * kA_SBO + (uint32_t)kq * kA_LBO + (uint32_t)(rsub & 7) * 16;
-        const uint32_t off1 = off0 + 8 * kA_SBO;
         int r = 0, rph = 0, q = 0, qph = 0;
         const long long tc0 = a.dbg ? clock64() : 0;
         for (int step = 0; step < total_steps; ++step) {
@@ -299,22 +302,22 @@ sparse_conv_pm_kernel(PmArgs a) {
                 mbar_wait(&raw_full[r], rph);
                 PM_ACC(1);
             }
-            const uint8_t* src = sRaw + (size_t)r * kATileBytes;
-            const float4 x0 = *reinterpret_cast<const float4*>(src + off0);
-            const float4 x1 = *reinterpret_cast<const float4*>(src + off1);
-            float4 l0, l1;
-            l0.x = x0.x - umma::tf32_hi(x0.x); l0.y = x0.y - umma::tf32_hi(x0.y);
-            l0.z = x0.z - umma::tf32_hi(x0.z); l0.w = x0.w - umma::tf32_hi(x0.w);
-            l1.x = x1.x - umma::tf32_hi(x1.x); l1.y = x1.y - umma::tf32_hi(x1.y);
-            l1.z = x1.z - umma::tf32_hi(x1.z); l1.w = x1.w - umma::tf32_hi(x1.w);
+            const uint8_t* src = sRaw + (size_t)r * kATileBytes + off0;
+            float4 l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 x = *reinterpret_cast<const float4*>(src + (uint32_t)j * 4 * kA_SBO);
+                l[j].x = x.x - umma::tf32_hi(x.x); l[j].y = x.y - umma::tf32_hi(x.y);
+                l[j].z = x.z - umma::tf32_hi(x.z); l[j].w = x.w - umma::tf32_hi(x.w);
+            }
             if (step >= Q) {
                 PM_T0();
                 mbar_wait(&lo_empty[q], qph ^ 1);
                 PM_ACC(12);
             }
-            uint8_t* dst = sLo + (size_t)q * kATileBytes;
-            *reinterpret_cast<float4*>(dst + off0) = l0;
-            *reinterpret_cast<float4*>(dst + off1) = l1;
+            uint8_t* dst = sLo + (size_t)q * kATileBytes + off0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(dst + (uint32_t)j * 4 * kA_SBO) = l[j];
             umma::fence_proxy_async();
             mbar_arrive(&lo_full[q]);
             if (++r == R) {
@@ -522,19 +525,13 @@ void sparse_conv_pm_tiles(const ConvPlan& P, const float* x, const float* wp, in
     const size_t budget = 226 * 1024;
     const size_t b_bytes = (size_t)a.nch * 2 * a.nc * KC * 4;
     a.Q = b_bytes > 64 * 1024 ? 2 : kMaxLo;
-    a.eb = std::min(a.nc, 64);
-    auto raw_stages = [&]() {
-        const size_t t_bytes = (size_t)TM * (a.eb + 4) * sizeof(float);
+    a.eb = std::min(a.nc / 2, 32);  // columns one epilogue thread stages per bulk reduction
+    const size_t t_bytes = (size_t)kEpiWarps * 32 * (a.eb + 4) * sizeof(float);
+    {
         const size_t fixed = b_bytes + (size_t)a.Q * kATileBytes + t_bytes;
-        return fixed >= budget ? 0 : (int)std::min<size_t>(kMaxRaw, (budget - fixed) / kATileBytes);
-    };
-    a.R = raw_stages();
-    if (a.R < 7 && a.eb > 32) {  // prefer a deeper gather ring over wide staging rows
-        a.eb = 32;
-        a.R = raw_stages();
+        a.R = fixed >= budget ? 0 : (int)std::min<size_t>(kMaxRaw, (budget - fixed) / kATileBytes);
     }
     ASRB_REQUIRE(a.R >= 3, "sparse_conv_pm: shared-memory budget");
-    const size_t t_bytes = (size_t)TM * (a.eb + 4) * sizeof(float);
     a.off_raw = (uint32_t)b_bytes;
     a.off_lo = (uint32_t)(b_bytes + (size_t)a.R * kATileBytes);
     a.off_t = (uint32_t)(a.off_lo + (size_t)a.Q * kATileBytes);
