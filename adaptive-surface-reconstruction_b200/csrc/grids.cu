@@ -75,69 +75,63 @@ __device__ __forceinline__ int second_round_face(int lane) {  // lane 0..29 -> p
     return p < 31 ? (p - 7) >> 2 : p - 31;
 }
 
-// pass 1: 55-bit slot mask per voxel
+// pass 1: 55-bit slot mask per voxel; the indices found are kept, in slot order, in `stash`
+// ([V][32] int32: a row has at most 1 + 6 x 4 = 25 entries), so pass 2 is a plain copy
 __global__ void __launch_bounds__(256)
 adjacency_mask_kernel(const Key* __restrict__ keys, long long V, const KeyTableView table,
-                      unsigned long long* __restrict__ mask, int32_t* __restrict__ count) {
+                      unsigned long long* __restrict__ mask, int32_t* __restrict__ count, int32_t* __restrict__ stash) {
     const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= V) return;
     const Cell c = key_cell(keys[w]);
     unsigned long long m = lane == 0 ? 1ULL : 0ULL;
-    bool same = false;
+    long long i1 = lane == 0 ? w : -1, i2 = -1;  // what this lane found in round 1 / round 2
+    int s1 = 0, s2 = 0;
     if (lane >= 1 && lane < 7) {
         const Probe pr = make_probe(c, lane);
-        same = pr.key && table_find(table, pr.key) >= 0;
-        if (same) m = 1ULL << lane;
+        if (pr.key) i1 = table_find(table, pr.key);
+        if (i1 >= 0) {
+            m = 1ULL << lane;
+            s1 = lane;
+        }
     }
-    const unsigned same_faces = __ballot_sync(0xffffffffu, same) >> 1;  // bit f = face f has a same-level neighbour
+    const unsigned same_faces = __ballot_sync(0xffffffffu, lane >= 1 && lane < 7 && i1 >= 0) >> 1;  // bit f: face f has a same-level neighbour
     if (lane < 30 && !((same_faces >> second_round_face(lane)) & 1)) {
         const Probe pr = make_probe(c, lane + 7);
-        if (pr.key && table_find(table, pr.key) >= 0) m |= 1ULL << pr.slot;
+        if (pr.key) i2 = table_find(table, pr.key);
+        if (i2 >= 0) {
+            m |= 1ULL << pr.slot;
+            s2 = pr.slot;
+        }
     }
-    unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)m);
-    unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(m >> 32));
+    const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)m);
+    const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(m >> 32));
+    m = ((unsigned long long)hi << 32) | lo;
+    int32_t* row = stash + w * 32;
+    if (i1 >= 0) row[__popcll(m & ((1ULL << s1) - 1))] = (int32_t)i1;
+    if (i2 >= 0) row[__popcll(m & ((1ULL << s2) - 1))] = (int32_t)i2;
     if (lane == 0) {
-        m = ((unsigned long long)hi << 32) | lo;
         mask[w] = m;
         count[w] = __popcll(m);
     }
 }
 
-// pass 2: write (index, slot) in slot order; only the slots present in the mask are looked up
+// pass 2: (index, slot) in slot order from the stash and the mask
 __global__ void __launch_bounds__(256)
-adjacency_fill_kernel(const Key* __restrict__ keys, long long V, const KeyTableView table,
-                      const unsigned long long* __restrict__ mask, const int64_t* __restrict__ splits,
-                      int32_t* __restrict__ nidx, uint8_t* __restrict__ nslot) {
+adjacency_fill_kernel(long long V, const unsigned long long* __restrict__ mask, const int32_t* __restrict__ stash,
+                      const int64_t* __restrict__ splits, int32_t* __restrict__ nidx, uint8_t* __restrict__ nslot) {
     const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= V) return;
     const unsigned long long m = mask[w];
-    const Cell c = key_cell(keys[w]);
+    const int cnt = __popcll(m);
+    if (lane >= cnt) return;
+    const unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
+    const int nlo = __popc(lo);
+    const int slot = lane < nlo ? (int)__fns(lo, 0, lane + 1) : 32 + (int)__fns(hi, 0, lane - nlo + 1);
     const int64_t base = splits[w];
-    auto emit = [&](int slot, long long idx) {
-        const int pos = __popcll(m & ((1ULL << slot) - 1));
-        nidx[base + pos] = (int32_t)idx;
-        nslot[base + pos] = (uint8_t)slot;
-    };
-    if (lane == 0) emit(0, w);
-    if (lane >= 1 && lane < 7 && ((m >> lane) & 1)) emit(lane, table_find(table, make_probe(c, lane).key));
-    if (lane < 30 && (m >> 7)) {
-        const int p = lane + 7;
-        bool want;
-        if (p < 31) {
-            want = (m >> p) & 1;
-        } else {  // a coarser slot is one of 31 + 4 f + {0..3}: any bit of the face's nibble
-            want = (m >> (31 + 4 * (p - 31))) & 0xF;
-        }
-        if (want) {
-            const Probe pr = make_probe(c, p);
-            if (pr.key && ((m >> pr.slot) & 1)) {
-                const long long idx = table_find(table, pr.key);
-                if (idx >= 0) emit(pr.slot, idx);
-            }
-        }
-    }
+    nidx[base + lane] = stash[w * 32 + lane];
+    nslot[base + lane] = (uint8_t)slot;
 }
 
 // ------------------------------------------------------------------ coarsening
@@ -202,10 +196,11 @@ static void build_adjacency(GridLevel& g, const KeyTable& table, cudaStream_t s)
     g.nsplits.alloc((size_t)V + 1, s);
     DevBuf<unsigned long long> mask((size_t)V, s);
     DevBuf<int32_t> count((size_t)V, s);
+    DevBuf<int32_t> stash((size_t)V * 32, s);
     if (V) {
         ProfileScope prof("adjacency_mask", s);
         adjacency_mask_kernel<<<grid_for((size_t)V * 32, 256), 256, 0, s>>>(g.keys.get(), V, table.view(), mask.get(),
-                                                                            count.get());
+                                                                            count.get(), stash.get());
         ASRB_CHECK_LAUNCH();
     }
     exclusive_sum_i32_to_i64(count.get(), g.nsplits.get(), (size_t)V, s);
@@ -214,9 +209,8 @@ static void build_adjacency(GridLevel& g, const KeyTable& table, cudaStream_t s)
     g.nslot.alloc((size_t)g.E, s);
     if (V) {
         ProfileScope prof("adjacency_fill", s);
-        adjacency_fill_kernel<<<grid_for((size_t)V * 32, 256), 256, 0, s>>>(g.keys.get(), V, table.view(), mask.get(),
-                                                                            g.nsplits.get(), g.nidx.get(),
-                                                                            g.nslot.get());
+        adjacency_fill_kernel<<<grid_for((size_t)V * 32, 256), 256, 0, s>>>(V, mask.get(), stash.get(), g.nsplits.get(),
+                                                                            g.nidx.get(), g.nslot.get());
         ASRB_CHECK_LAUNCH();
     }
 }

@@ -209,13 +209,38 @@ cell_end_kernel(const Key* __restrict__ codes, long long n, unsigned levels, Has
     }
 }
 
+constexpr int kStash = 32;
+
+// rows of <= kStash hits: rank sort of the stashed (d2, index) keys straight into the result
+__global__ void __launch_bounds__(256)
+stash_rows_kernel(const unsigned long long* __restrict__ stash, const int64_t* __restrict__ splits, long long nq,
+                  int32_t* __restrict__ out_idx, float* __restrict__ out_d2) {
+    const long long q = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const int64_t b = splits[q];
+    const int n = (int)(splits[q + 1] - b);
+    if (n == 0 || n > kStash) return;
+    const unsigned long long mine = lane < n ? stash[q * kStash + lane] : ~0ULL;
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += __shfl_sync(0xffffffffu, mine, j) < mine ? 1 : 0;
+    if (lane < n) {
+        out_idx[b + rank] = (int32_t)(unsigned)mine;
+        out_d2[b + rank] = __uint_as_float((unsigned)(mine >> 32));
+    }
+}
+
 template <bool FILL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 ball_query_kernel(const KeyTableView cells, const float4* __restrict__ spts, BinFrame f,
                   const float* __restrict__ queries, const float* __restrict__ radii, long long nq,
                   int32_t* __restrict__ counts, const int64_t* __restrict__ splits,
                   unsigned long long* __restrict__ out_keys, int32_t* __restrict__ out_idx,
-                  float* __restrict__ out_d2) {
+                  float* __restrict__ out_d2, unsigned long long* __restrict__ stash) {
+    // count pass (FILL = false): the first kStash hits of every query are also kept in `stash`
+    // ([nq][kStash] keys), so rows of <= kStash hits (nearly all) are finished by
+    // stash_rows_kernel without streaming the candidates again; the fill pass (FILL = true)
+    // then only redoes the longer rows (skip_small: stash != nullptr).
     __shared__ unsigned s_begin[kWarpsPerBlock][32];
     __shared__ int s_pre[kWarpsPerBlock][33];
     __shared__ unsigned long long s_hit[FILL ? kWarpsPerBlock : 1][32];
@@ -223,6 +248,7 @@ ball_query_kernel(const KeyTableView cells, const float4* __restrict__ spts, Bin
     const long long q = blockIdx.x * (long long)kWarpsPerBlock + warp;
     if (q >= nq) return;
     const float qx = queries[3 * q], qy = queries[3 * q + 1], qz = queries[3 * q + 2];
+    if (FILL && stash && splits[q + 1] - splits[q] <= kStash) return;
     const float r = radii[q];
     const float r2 = __fmul_rn(r, r);
     int len = 0;
@@ -280,6 +306,10 @@ ball_query_kernel(const KeyTableView cells, const float4* __restrict__ spts, Bin
             const int pos = found + __popc(m & ((1u << lane) - 1));
             if (small) s_hit[warp][pos] = key;
             else out_keys[out_base + pos] = key;
+        }
+        if (!FILL && stash && hit) {
+            const int pos = found + __popc(m & ((1u << lane) - 1));
+            if (pos < kStash) stash[q * kStash + pos] = key;
         }
         found += __popc(m);
     }
@@ -402,14 +432,15 @@ void search_prepare(Search& S, const float* d_points, int64_t n, const float* d_
             ASRB_CHECK_LAUNCH();
         }
     }
-    // count pass
+    // count pass (stashing the first kStash hits per query when the results will be asked for)
     DevBuf<int32_t> counts((size_t)nq, s);
+    if (S.want_fill) S.stash.alloc((size_t)nq * kStash, s);
     S.splits.alloc((size_t)nq + 1, s);
     if (nq > 0) {
         ProfileScope prof("ball_query_count", s);
         ball_query_kernel<false><<<grid_for(nq, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
                 S.cells.view(), (const float4*)S.spts.get(), f, d_queries, d_radii, nq, counts.get(), nullptr, nullptr, nullptr,
-                nullptr);
+                nullptr, S.stash.get());
         ASRB_CHECK_LAUNCH();
     }
     exclusive_sum_i32_to_i64(counts.get(), S.splits.get(), (size_t)nq, s);
@@ -423,10 +454,15 @@ void search_fill(Search& S, int32_t* d_idx, float* d_d2, int64_t* d_splits, cuda
     if (S.nq == 0 || S.num_pairs == 0) return;
     DevBuf<unsigned long long> keys((size_t)S.num_pairs, s);
     ProfileScope prof("ball_query_fill_sort", s);
+    if (S.stash.size()) {
+        stash_rows_kernel<<<grid_for((size_t)S.nq * 32, 256), 256, 0, s>>>(S.stash.get(), S.splits.get(), S.nq, d_idx, d_d2);
+        ASRB_CHECK_LAUNCH();
+    }
     ball_query_kernel<true><<<grid_for(S.nq, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
             S.cells.view(), (const float4*)S.spts.get(), f, S.queries, S.radii, S.nq, nullptr, S.splits.get(), keys.get(),
-            d_idx, d_d2);
+            d_idx, d_d2, S.stash.size() ? S.stash.get() : nullptr);
     ASRB_CHECK_LAUNCH();
+    S.stash.release();
 }
 
 void scale_compat(const float* d_sizes, const float* d_radii, const int32_t* d_idx, const int64_t* d_splits,
@@ -644,6 +680,7 @@ void knn_inlier(const Search& S, const float* d_radii, float fraction, int k, in
 void radius_neighbor_counts(const float* d_points, int64_t n, const float* d_radii, int32_t* d_out, cudaStream_t s) {
     if (n == 0) return;
     Search S;
+    S.want_fill = false;  // counts only
     search_prepare(S, d_points, n, d_points, d_radii, n, nullptr, s);
     row_counts_kernel<<<grid_for(n, 256), 256, 0, s>>>(S.splits.get(), n, d_out);
     ASRB_CHECK_LAUNCH();

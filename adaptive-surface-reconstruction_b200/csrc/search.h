@@ -18,6 +18,8 @@ struct Search {
     DevBuf<Float4Pod> spts;  // points in sorted order, w = original index bits
     KeyTable cells;          // (cell code | level marker) -> begin | end << 32 in the sorted points
     DevBuf<int64_t> splits;  // [nq+1]
+    bool want_fill = true;   // keep the first hits of every query from the count pass (search_fill follows)
+    DevBuf<unsigned long long> stash;
 };
 
 void search_prepare(Search& S, const float* d_points, int64_t n, const float* d_queries, const float* d_radii,
