@@ -209,9 +209,10 @@ cell_end_kernel(const Key* __restrict__ codes, long long n, unsigned levels, Has
     }
 }
 
-constexpr int kStash = 32;
+constexpr int kStash = 64;
 
 // rows of <= kStash hits: rank sort of the stashed (d2, index) keys straight into the result
+// (a lane holds keys `lane` and `lane + 32`)
 __global__ void __launch_bounds__(256)
 stash_rows_kernel(const unsigned long long* __restrict__ stash, const int64_t* __restrict__ splits, long long nq,
                   int32_t* __restrict__ out_idx, float* __restrict__ out_d2) {
@@ -221,12 +222,26 @@ stash_rows_kernel(const unsigned long long* __restrict__ stash, const int64_t* _
     const int64_t b = splits[q];
     const int n = (int)(splits[q + 1] - b);
     if (n == 0 || n > kStash) return;
-    const unsigned long long mine = lane < n ? stash[q * kStash + lane] : ~0ULL;
-    int rank = 0;
-    for (int j = 0; j < n; ++j) rank += __shfl_sync(0xffffffffu, mine, j) < mine ? 1 : 0;
+    const unsigned long long m0 = lane < n ? stash[q * kStash + lane] : ~0ULL;
+    const unsigned long long m1 = lane + 32 < n ? stash[q * kStash + 32 + lane] : ~0ULL;
+    int r0 = 0, r1 = 0;
+    for (int j = 0; j < min(n, 32); ++j) {
+        const unsigned long long k = __shfl_sync(0xffffffffu, m0, j);
+        r0 += k < m0 ? 1 : 0;
+        r1 += k < m1 ? 1 : 0;
+    }
+    for (int j = 32; j < n; ++j) {
+        const unsigned long long k = __shfl_sync(0xffffffffu, m1, j - 32);
+        r0 += k < m0 ? 1 : 0;
+        r1 += k < m1 ? 1 : 0;
+    }
     if (lane < n) {
-        out_idx[b + rank] = (int32_t)(unsigned)mine;
-        out_d2[b + rank] = __uint_as_float((unsigned)(mine >> 32));
+        out_idx[b + r0] = (int32_t)(unsigned)m0;
+        out_d2[b + r0] = __uint_as_float((unsigned)(m0 >> 32));
+    }
+    if (lane + 32 < n) {
+        out_idx[b + r1] = (int32_t)(unsigned)m1;
+        out_d2[b + r1] = __uint_as_float((unsigned)(m1 >> 32));
     }
 }
 

@@ -86,19 +86,23 @@ __device__ __forceinline__ long long lower_bound_u32(const uint32_t* a, long lon
     return lo;
 }
 
-// one block: (row block, slot) run boundaries, then the tile list (slot, first pair, count)
+// first pair of every (row block, slot) group: one binary search per thread, whole grid
+__global__ void __launch_bounds__(256)
+group_begin_kernel(const uint32_t* __restrict__ sorted_key, long long E, int K, int G, long long* __restrict__ g_begin) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > G) return;
+    const uint32_t key = ((uint32_t)(g / K) << 8) | (uint32_t)(g % K);
+    g_begin[g] = g == G ? E : lower_bound_u32(sorted_key, E, key);
+}
+
+// one block: the tile list (slot, first pair, count)
 // for tiles of `tile_rows` pairs.  Prefix over the groups: per-thread chunks + a 256-entry scan.
 __global__ void __launch_bounds__(256)
 tile_list_kernel(const uint32_t* __restrict__ sorted_key, long long E, int K, int num_blocks, int tile_rows,
                  long long* __restrict__ g_begin, int* __restrict__ g_tile0, int4* __restrict__ tiles,
                  int* __restrict__ num_tiles) {
     __shared__ int s_part[256];
-    const int G = num_blocks * K;
-    for (int g = threadIdx.x; g <= G; g += blockDim.x) {
-        const uint32_t key = ((uint32_t)(g / K) << 8) | (uint32_t)(g % K);
-        g_begin[g] = g == G ? E : lower_bound_u32(sorted_key, E, key);
-    }
-    __syncthreads();
+    const int G = num_blocks * K;  // g_begin comes from group_begin_kernel
     const int chunk = (G + 255) / 256;
     const int g0 = min(G, (int)threadIdx.x * chunk), g1 = min(G, g0 + chunk);
     int sum = 0;
@@ -163,12 +167,13 @@ void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, c
                                                              P.p_out.get());
         ASRB_CHECK_LAUNCH();
     }
+    group_begin_kernel<<<grid_for((size_t)G + 1, 256), 256, 0, s>>>(keys.get(), E, K, G, g_begin.get());
+    ASRB_CHECK_LAUNCH();
     tile_list_kernel<<<1, 256, 0, s>>>(keys.get(), E, K, std::max(num_blocks, 1), TM, g_begin.get(), g_tile0.get(),
                                        (int4*)P.tiles.get(), P.num_tiles.get());
     ASRB_CHECK_LAUNCH();
     if (sparse_conv_tc_row_groups() == 2) {
-        DevBuf<long long> g_begin2((size_t)G + 1, s);
-        tile_list_kernel<<<1, 256, 0, s>>>(keys.get(), E, K, std::max(num_blocks, 1), 2 * TM, g_begin2.get(),
+        tile_list_kernel<<<1, 256, 0, s>>>(keys.get(), E, K, std::max(num_blocks, 1), 2 * TM, g_begin.get(),
                                            nullptr, (int4*)P.tiles2.get(), P.num_tiles2.get());
         ASRB_CHECK_LAUNCH();
         P.has_tiles2 = true;
