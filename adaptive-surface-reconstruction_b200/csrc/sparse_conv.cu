@@ -50,18 +50,43 @@ constexpr int kThreads = 256;  // 16 x 16
 // are processed, and W[slot] is still reused by whole 128-pair tiles.
 constexpr int kRowBlockShift = 15;
 
+// Sort key of an entry: slot-0 entries first (bit `kb`), then (row block, slot).  With the self
+// slot first, and every row owning exactly one slot-0 entry (all within-grid tables), the
+// slot-0 tiles can STORE their rows — that initialises the whole output, so neither a zero
+// fill nor reductions are needed for 1/8 of the pairs (sparse_conv_forward).
 __global__ void __launch_bounds__(256)
-entry_rows_kernel(const int64_t* __restrict__ splits, long long V, const uint8_t* __restrict__ slot,
-                  uint32_t* __restrict__ rows, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+entry_rows_kernel(const int64_t* __restrict__ splits, long long V, const uint8_t* __restrict__ slot, int kb,
+                  uint32_t* __restrict__ rows, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                  int* __restrict__ not_one_slot0) {
     const long long v = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3;
     const int sub = threadIdx.x & 7;
-    if (v >= V) return;
-    const int64_t e = splits[v + 1];
-    const uint32_t hi = (uint32_t)(v >> kRowBlockShift) << 8;
-    for (int64_t j = splits[v] + sub; j < e; j += 8) {
-        rows[j] = (uint32_t)v;
-        keys[j] = hi | slot[j];
-        vals[j] = (uint32_t)j;
+    int n0 = 0;
+    if (v < V) {
+        const int64_t e = splits[v + 1];
+        const uint32_t hi = (uint32_t)(v >> kRowBlockShift) << 8;
+        for (int64_t j = splits[v] + sub; j < e; j += 8) {
+            const uint32_t k = slot[j];
+            rows[j] = (uint32_t)v;
+            keys[j] = (k ? (1u << kb) : 0u) | hi | k;
+            vals[j] = (uint32_t)j;
+            n0 += k == 0;
+        }
+    }
+    n0 += __shfl_xor_sync(0xffffffffu, n0, 1);
+    n0 += __shfl_xor_sync(0xffffffffu, n0, 2);
+    n0 += __shfl_xor_sync(0xffffffffu, n0, 4);
+    if (v < V && sub == 0 && n0 != 1) *not_one_slot0 = 1;
+}
+
+// groups in sorted order: g < num_blocks -> (block g, slot 0); then per block the slots 1 .. K-1
+__host__ __device__ __forceinline__ void group_block_slot(int g, int K, int num_blocks, int& block, int& slot) {
+    if (g < num_blocks) {
+        block = g;
+        slot = 0;
+    } else {
+        const int r = g - num_blocks;
+        block = r / (K - 1);
+        slot = 1 + r % (K - 1);
     }
 }
 
@@ -86,23 +111,29 @@ __device__ __forceinline__ long long lower_bound_u32(const uint32_t* a, long lon
     return lo;
 }
 
-// first pair of every (row block, slot) group: one binary search per thread, whole grid
+// first pair of every group: one binary search per thread, whole grid
 __global__ void __launch_bounds__(256)
-group_begin_kernel(const uint32_t* __restrict__ sorted_key, long long E, int K, int G, long long* __restrict__ g_begin) {
+group_begin_kernel(const uint32_t* __restrict__ sorted_key, long long E, int K, int num_blocks, int kb, int G,
+                   long long* __restrict__ g_begin) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g > G) return;
-    const uint32_t key = ((uint32_t)(g / K) << 8) | (uint32_t)(g % K);
-    g_begin[g] = g == G ? E : lower_bound_u32(sorted_key, E, key);
+    if (g == G) {
+        g_begin[g] = E;
+        return;
+    }
+    int block, slot;
+    group_block_slot(g, K, num_blocks, block, slot);
+    const uint32_t key = (slot ? (1u << kb) : 0u) | ((uint32_t)block << 8) | (uint32_t)slot;
+    g_begin[g] = lower_bound_u32(sorted_key, E, key);
 }
 
-// one block: the tile list (slot, first pair, count)
-// for tiles of `tile_rows` pairs.  Prefix over the groups: per-thread chunks + a 256-entry scan.
+// one block: the tile list (slot, first pair, count) for tiles of `tile_rows` pairs.  Prefix over
+// the groups: per-thread chunks + a 256-entry scan.
 __global__ void __launch_bounds__(256)
-tile_list_kernel(const uint32_t* __restrict__ sorted_key, long long E, int K, int num_blocks, int tile_rows,
-                 long long* __restrict__ g_begin, int* __restrict__ g_tile0, int4* __restrict__ tiles,
-                 int* __restrict__ num_tiles) {
+tile_list_kernel(int K, int num_blocks, int tile_rows, const long long* __restrict__ g_begin, int* __restrict__ g_tile0,
+                 int4* __restrict__ tiles, int* __restrict__ num_tiles) {
     __shared__ int s_part[256];
-    const int G = num_blocks * K;  // g_begin comes from group_begin_kernel
+    const int G = num_blocks * K;
     const int chunk = (G + 255) / 256;
     const int g0 = min(G, (int)threadIdx.x * chunk), g1 = min(G, g0 + chunk);
     int sum = 0;
@@ -124,8 +155,10 @@ tile_list_kernel(const uint32_t* __restrict__ sorted_key, long long E, int K, in
     for (int g = g0; g < g1; ++g) {
         const long long b = g_begin[g], e = g_begin[g + 1];
         if (g_tile0) g_tile0[g] = t;
+        int block, slot;
+        group_block_slot(g, K, num_blocks, block, slot);
         for (long long start = b; start < e; start += tile_rows)
-            tiles[t++] = make_int4(g % K, (int)start, (int)min((long long)tile_rows, e - start), 0);
+            tiles[t++] = make_int4(slot, (int)start, (int)min((long long)tile_rows, e - start), 0);
     }
 }
 
@@ -156,27 +189,41 @@ void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, c
     P.g_tile0.alloc((size_t)G + 1, s);
     DevBuf<long long>& g_begin = P.g_begin;
     DevBuf<int>& g_tile0 = P.g_tile0;
+    int bits = 8;
+    while (bits < 31 && (int64_t(1) << (bits - 8)) < std::max(num_blocks, 1)) ++bits;
+    P.num_blocks = std::max(num_blocks, 1);
+    DevBuf<int> flag(1, s);
+    ASRB_CUDA(cudaMemsetAsync(flag.get(), 0, sizeof(int), s));
     if (E) {
-        entry_rows_kernel<<<grid_for((size_t)V_out * 8, 256), 256, 0, s>>>(d_splits, V_out, d_slot, rows.get(),
-                                                                          keys.get(), P.perm.get());
+        entry_rows_kernel<<<grid_for((size_t)V_out * 8, 256), 256, 0, s>>>(d_splits, V_out, d_slot, bits, rows.get(),
+                                                                          keys.get(), P.perm.get(), flag.get());
         ASRB_CHECK_LAUNCH();
-        int bits = 8;
-        while (bits < 32 && (int64_t(1) << (bits - 8)) < std::max(num_blocks, 1)) ++bits;
-        sort_pairs_u32_u32(keys.get(), P.perm.get(), (size_t)E, s, bits);
+        sort_pairs_u32_u32(keys.get(), P.perm.get(), (size_t)E, s, bits + 1);
         gather_pairs_kernel<<<grid_for(E, 256), 256, 0, s>>>(P.perm.get(), rows.get(), d_idx, E, P.p_in.get(),
                                                              P.p_out.get());
         ASRB_CHECK_LAUNCH();
     }
-    group_begin_kernel<<<grid_for((size_t)G + 1, 256), 256, 0, s>>>(keys.get(), E, K, G, g_begin.get());
+    group_begin_kernel<<<grid_for((size_t)G + 1, 256), 256, 0, s>>>(keys.get(), E, K, P.num_blocks, bits, G,
+                                                                   g_begin.get());
     ASRB_CHECK_LAUNCH();
-    tile_list_kernel<<<1, 256, 0, s>>>(keys.get(), E, K, std::max(num_blocks, 1), TM, g_begin.get(), g_tile0.get(),
-                                       (int4*)P.tiles.get(), P.num_tiles.get());
+    tile_list_kernel<<<1, 256, 0, s>>>(K, P.num_blocks, TM, g_begin.get(), g_tile0.get(), (int4*)P.tiles.get(),
+                                       P.num_tiles.get());
     ASRB_CHECK_LAUNCH();
     if (sparse_conv_tc_row_groups() == 2) {
-        tile_list_kernel<<<1, 256, 0, s>>>(keys.get(), E, K, std::max(num_blocks, 1), 2 * TM, g_begin.get(),
-                                           nullptr, (int4*)P.tiles2.get(), P.num_tiles2.get());
+        tile_list_kernel<<<1, 256, 0, s>>>(K, P.num_blocks, 2 * TM, g_begin.get(), nullptr, (int4*)P.tiles2.get(),
+                                           P.num_tiles2.get());
         ASRB_CHECK_LAUNCH();
         P.has_tiles2 = true;
+    }
+    // every row has exactly one slot-0 entry: its tiles are the first `tiles0` of the list and cover
+    // every output row once (rows per block / 128, rounded up per block)
+    P.tiles0 = 0;
+    if (E && K > 1 && !d2h_scalar(flag.get(), s)) {
+        const int64_t rows_per_block = int64_t(1) << kRowBlockShift;
+        for (int b = 0; b < P.num_blocks; ++b) {
+            const int64_t r = std::min<int64_t>(rows_per_block, V_out - b * rows_per_block);
+            P.tiles0 += (int)((r + TM - 1) / TM);
+        }
     }
 
     if (with_output_stationary && sparse_conv_os_enabled() && K == 55 && V_out > 0)
@@ -458,14 +505,16 @@ void sparse_conv_forward(const ConvPlan& P, const float* x, const float* w, cons
         }
         return;
     }
-    {
+    const bool store_first = wp && P.E > 0 && P.tiles0 > 0 && sparse_conv_tc_row_groups() == 1 &&
+                             !sparse_conv_pm_supported(P, Cin, Cout);
+    if (!store_first) {
         ProfileScope prof("sparse_conv_zero", s);
         ASRB_CUDA(cudaMemsetAsync(out, 0, (size_t)P.V_out * Cout * sizeof(float), s));
     }
     if (P.E > 0 && wp && sparse_conv_pm_supported(P, Cin, Cout)) {
         sparse_conv_pm_tiles(P, x, wp, Cin, Cout, imp_in, imp_entry, imp_col, out, s);
     } else if (P.E > 0 && wp) {
-        sparse_conv_tc_tiles(P, x, wp, Cin, Cout, imp_in, imp_entry, imp_col, out, s);
+        sparse_conv_tc_tiles(P, x, wp, Cin, Cout, imp_in, imp_entry, imp_col, out, s, store_first);
     } else if (P.E > 0) {
         TileArgs a;
         a.x = x;

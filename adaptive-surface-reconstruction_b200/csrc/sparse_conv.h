@@ -20,7 +20,8 @@ struct ConvPlan {
     DevBuf<int> num_tiles;        // device scalar
     // (row block, slot) groups, g = block * K + slot: first pair and number of 128-pair tiles
     // before each group ([G + 1] each); the persistent kernel walks these instead of `tiles`
-    int G = 0;
+    int G = 0, num_blocks = 1;
+    int tiles0 = 0;  // > 0: the first tiles0 tiles are the slot-0 tiles and cover every output row exactly once
     DevBuf<long long> g_begin;
     DevBuf<int> g_tile0;
     bool has_tiles2 = false;      // built only when the 2-row-group option is on at plan creation
@@ -54,8 +55,9 @@ void sparse_conv_forward(const ConvPlan& P, const float* x, const float* w, cons
 
 size_t packed_conv_filters_floats(int K, int Cin, int Cout);
 void pack_conv_filters(const float* W, int K, int Cin, int Cout, float* out, cudaStream_t s);
+// store_first: `out` is NOT zero-initialised; the slot-0 tiles (P.tiles0 > 0) write it first
 void sparse_conv_tc_tiles(const ConvPlan& P, const float* x, const float* wp, int Cin, int Cout, const float* imp_in,
-                          const float* imp_entry, int imp_col, float* out, cudaStream_t s);
+                          const float* imp_entry, int imp_col, float* out, cudaStream_t s, bool store_first = false);
 
 // persistent pair-major tensor-core kernel (sparse_conv_pm.cu): filter part resident in shared
 // memory, TMEM double buffering, bulk-reduction epilogue

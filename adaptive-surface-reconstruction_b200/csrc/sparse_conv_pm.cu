@@ -67,7 +67,7 @@ struct PmArgs {
     const float* imp_in;
     const float* imp_entry;
     float* out;
-    int G, K;
+    int G, K, num_blocks;  // groups in sorted order: (block, slot 0) for all blocks, then per block slots 1..K-1
     int Cin, Cout, n_pad, imp_col;
     int nparts;   // column parts; part index p = kpart * nparts + npart
     int parts;    // kparts * nparts
@@ -409,7 +409,7 @@ sparse_conv_pm_kernel(PmArgs a) {
         int r = 0, q = 0, qph = 0;
         for (int n = 0; n < n_items; ++n) {
             const int buf = n & 1, use = n >> 1;
-            const int slot = it.g % a.K, p = it.p;
+            const int slot = it.g < a.num_blocks ? 0 : 1 + (it.g - a.num_blocks) % (a.K - 1), p = it.p;
             bool wait_b = false;
             if (slot != cur_slot || p != cur_p) {
                 // every MMA issued so far has read the old filter part: wait for the last commit
@@ -512,6 +512,7 @@ void sparse_conv_pm_tiles(const ConvPlan& P, const float* x, const float* wp, in
     a.out = out;
     a.G = P.G;
     a.K = P.K;
+    a.num_blocks = P.num_blocks;
     a.Cin = Cin;
     a.Cout = Cout;
     a.n_pad = Cout;

@@ -61,6 +61,8 @@ struct TcArgs {
     float* out;
     int Cin, Cout, n_pad, imp_col, stages;
     int n_tile;  // output channels handled by one CTA (n_pad, or 128 with blockIdx.y selecting the half)
+    int tile0, tile1;  // tiles [tile0, min(tile1, *num_tiles)) of the list
+    int store;         // 1: the tiles' rows are written (slot-0 tiles covering every row once), 0: reduced
 };
 
 // MT = number of 128-row MMA groups per CTA (tile = 128 * MT pairs).  MT = 2 halves the
@@ -91,8 +93,9 @@ sparse_conv_tc_kernel(TcArgs a) {
     __shared__ int s_out[TMC];
     __shared__ float s_imp[TMC];
 
-    if ((int)blockIdx.x >= *a.num_tiles) return;
-    const int4 tile = a.tiles[blockIdx.x];
+    const int tile_id = a.tile0 + (int)blockIdx.x;
+    if (tile_id >= min(a.tile1, *a.num_tiles)) return;
+    const int4 tile = a.tiles[tile_id];
     const int slot = tile.x, start = tile.y, count = tile.z;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int S = a.stages;
@@ -219,7 +222,10 @@ sparse_conv_tc_kernel(TcArgs a) {
         umma::fence_proxy_async();  // generic-proxy writes of this thread -> visible to the bulk (async proxy) read
         const int o = s_out[prow];
         const int ncol = min(NT, a.Cout - col0);
-        if (o >= 0 && ncol > 0) umma::bulk_reduce_add_f32(a.out + (size_t)o * a.Cout + col0, T, (uint32_t)ncol * 4);
+        if (o >= 0 && ncol > 0) {
+            if (a.store) umma::bulk_store(a.out + (size_t)o * a.Cout + col0, T, (uint32_t)ncol * 4);
+            else umma::bulk_reduce_add_f32(a.out + (size_t)o * a.Cout + col0, T, (uint32_t)ncol * 4);
+        }
         umma::bulk_commit();
         umma::bulk_wait_read();  // the staging rows live in this CTA's shared memory
     } else if ((tid & 31) == 0) {
@@ -311,7 +317,7 @@ void pack_conv_filters(const float* W, int K, int Cin, int Cout, float* out, cud
 }
 
 void sparse_conv_tc_tiles(const ConvPlan& P, const float* x, const float* wp, int Cin, int Cout, const float* imp_in,
-                          const float* imp_entry, int imp_col, float* out, cudaStream_t s) {
+                          const float* imp_entry, int imp_col, float* out, cudaStream_t s, bool store_first) {
     ASRB_REQUIRE(Cout <= 256, "tensor-core sparse conv: out_channels must be <= 256");
     const int n_pad = ((Cout + 15) / 16) * 16;
     TcArgs a;
@@ -340,14 +346,27 @@ void sparse_conv_tc_tiles(const ConvPlan& P, const float* x, const float* wp, in
     snprintf(label, sizeof(label), "sparse_conv_tile/tc K%d %dx%d E%lld", P.K, Cin, Cout, (long long)P.E);
     ProfileScope prof(label, s, 2.0 * (double)P.E * Cin * Cout);
     const unsigned ny = (unsigned)(n_pad / a.n_tile);
-    auto launch = [&](auto kernel, int max_tiles, int threads) {
+    auto launch = [&](auto kernel, int tiles, int threads) {
+        if (tiles <= 0) return;
         ASRB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kernel<<<dim3((unsigned)max_tiles, ny), threads, smem, s>>>(a);
+        kernel<<<dim3((unsigned)tiles, ny), threads, smem, s>>>(a);
+        ASRB_CHECK_LAUNCH();
     };
-    if (MT == 2) launch(sparse_conv_tc_kernel<2, 4>, P.max_tiles2, 288);
-    else if (Cin <= 64) launch(sparse_conv_tc_kernel<1, 2>, P.max_tiles, 160);
-    else launch(sparse_conv_tc_kernel<1, 4>, P.max_tiles, 160);
-    ASRB_CHECK_LAUNCH();
+    auto run = [&](int t0, int t1, int store) {
+        a.tile0 = t0;
+        a.tile1 = t1;
+        a.store = store;
+        if (MT == 2) launch(sparse_conv_tc_kernel<2, 4>, t1 - t0, 288);
+        else if (Cin <= 64) launch(sparse_conv_tc_kernel<1, 2>, t1 - t0, 160);
+        else launch(sparse_conv_tc_kernel<1, 4>, t1 - t0, 160);
+    };
+    const int max_tiles = MT == 2 ? P.max_tiles2 : P.max_tiles;
+    if (store_first && MT == 1 && P.tiles0 > 0) {
+        run(0, P.tiles0, 1);          // slot-0 tiles: write every output row (no zero fill needed)
+        run(P.tiles0, max_tiles, 0);  // all other slots: reduce into the written rows
+    } else {
+        run(0, max_tiles, 0);
+    }
 }
 
 }  // namespace asrb
