@@ -45,11 +45,11 @@ def _run(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_sharded_pipeline_matches_single_process():
-    world = 2
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_pipeline_matches_single_process(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 400)
+    port = 29500 + (os.getpid() % 400) + world
     procs = [ctx.Process(target=_run, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
