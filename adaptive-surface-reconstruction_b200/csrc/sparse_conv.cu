@@ -216,14 +216,25 @@ void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, c
         P.has_tiles2 = true;
     }
     // every row has exactly one slot-0 entry: its tiles are the first `tiles0` of the list and cover
-    // every output row once (rows per block / 128, rounded up per block)
+    // every output row once (rows per block / 128, rounded up per block).  The flag travels to a
+    // pinned host slot asynchronously and is read at the first convolution (no stall here).
     P.tiles0 = 0;
-    if (E && K > 1 && !d2h_scalar(flag.get(), s)) {
+    P.tiles0_if_flag = 0;
+    if (E && K > 1) {
         const int64_t rows_per_block = int64_t(1) << kRowBlockShift;
         for (int b = 0; b < P.num_blocks; ++b) {
             const int64_t r = std::min<int64_t>(rows_per_block, V_out - b * rows_per_block);
-            P.tiles0 += (int)((r + TM - 1) / TM);
+            P.tiles0_if_flag += (int)((r + TM - 1) / TM);
         }
+        static int* pool = nullptr;
+        static unsigned next = 0;
+        if (!pool) ASRB_CUDA(cudaMallocHost((void**)&pool, 1024 * sizeof(int)));
+        P.flag_host = pool + (next++ % 1024);
+        *P.flag_host = 1;
+        if (!P.flag_event) ASRB_CUDA(cudaEventCreateWithFlags(&P.flag_event, cudaEventDisableTiming));
+        ASRB_CUDA(cudaMemcpyAsync(P.flag_host, flag.get(), sizeof(int), cudaMemcpyDeviceToHost, s));
+        ASRB_CUDA(cudaEventRecord(P.flag_event, s));
+        P.flag_pending = true;
     }
 
     if (with_output_stationary && sparse_conv_os_enabled() && K == 55 && V_out > 0)
@@ -504,6 +515,11 @@ void sparse_conv_forward(const ConvPlan& P, const float* x, const float* w, cons
             }
         }
         return;
+    }
+    if (P.flag_pending) {
+        ASRB_CUDA(cudaEventSynchronize(P.flag_event));
+        P.tiles0 = *P.flag_host ? 0 : P.tiles0_if_flag;
+        P.flag_pending = false;
     }
     const bool store_first = wp && P.E > 0 && P.tiles0 > 0 && sparse_conv_tc_row_groups() == 1 &&
                              !sparse_conv_pm_supported(P, Cin, Cout);

@@ -21,7 +21,15 @@ struct ConvPlan {
     // (row block, slot) groups, g = block * K + slot: first pair and number of 128-pair tiles
     // before each group ([G + 1] each); the persistent kernel walks these instead of `tiles`
     int G = 0, num_blocks = 1;
-    int tiles0 = 0;  // > 0: the first tiles0 tiles are the slot-0 tiles and cover every output row exactly once
+    // > 0: the first tiles0 tiles are the slot-0 tiles and cover every output row exactly once
+    mutable int tiles0 = 0;
+    int tiles0_if_flag = 0;
+    mutable bool flag_pending = false;  // the device flag is still on its way to *flag_host
+    int* flag_host = nullptr;
+    cudaEvent_t flag_event = nullptr;
+    ~ConvPlan() {
+        if (flag_event) cudaEventDestroy(flag_event);
+    }
     DevBuf<long long> g_begin;
     DevBuf<int> g_tile0;
     bool has_tiles2 = false;      // built only when the 2-row-group option is on at plan creation
