@@ -107,10 +107,13 @@ cconv4_kernel(const float* __restrict__ filters, const float* __restrict__ out_p
     for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) Ws[i] = filters[i];
     __syncthreads();
     float* Bw = Bs + (size_t)warp * kCcGroup * K;
+    float* stage = Bs + (size_t)kCc4Warps * kCcGroup * K + warp * 256;  // [32 neighbours][8]
     const float ox = offset ? offset[0] : 0.f, oy = offset ? offset[1] : 0.f, oz = offset ? offset[2] : 0.f;
     const float sm1 = (float)(S - 1);
     const int tap = lane >> 2, ch = lane & 3;
     const int tx = tap & 1, ty = (tap >> 1) & 1, tz = tap >> 2;
+    const int tapmask = (tx << 8) | (ty << 9) | (tz << 10);  // flags that make this lane's tap a duplicate
+    const int tapoff = (tz * S + ty) * S + tx;               // cell offset of this lane's tap
     const long long nwarps = (long long)gridDim.x * kCc4Warps;
     long long gv[kCcGroup];
     float gnorm[kCcGroup];
@@ -168,23 +171,31 @@ cconv4_kernel(const float* __restrict__ filters, const float* __restrict__ out_p
         const float scale = 2.0f / extents[v * extents_stride];
         for (int64_t n0 = b; n0 < e; n0 += 32) {
             const int cnt = (int)min((int64_t)32, e - n0);
-            // ---- phase A: lane = neighbour
-            float x = 0.f, y = 0.f, z = 0.f, imp = 0.f, nimp_l = 0.f;
+            // ---- phase A: lane = neighbour.  Everything that depends only on the neighbour is
+            // computed here once: the base cell of its 2x2x2 taps (+ flags for taps clamped onto
+            // their twin), the three interpolation fractions and the weighted features.
+            float ax = 0.f, ay = 0.f, az = 0.f, nimp_l = 0.f;
+            int cellinfo = 0;  // base cell | (x0 == S-1) << 8 | (y0 == S-1) << 9 | (z0 == S-1) << 10
             float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
             if (lane < cnt) {
                 const int p = nidx[n0 + lane];
                 nimp_l = nimp ? nimp[n0 + lane] : 1.0f;
-                imp = inp_importance ? nimp_l * inp_importance[p] : nimp_l;
+                const float imp = inp_importance ? nimp_l * inp_importance[p] : nimp_l;
                 f = __ldg(inp_feat + p);
-                x = (inp_pos[3 * (size_t)p] - cx) * scale;
-                y = (inp_pos[3 * (size_t)p + 1] - cy) * scale;
-                z = (inp_pos[3 * (size_t)p + 2] - cz) * scale;
+                float x = (inp_pos[3 * (size_t)p] - cx) * scale;
+                float y = (inp_pos[3 * (size_t)p + 1] - cy) * scale;
+                float z = (inp_pos[3 * (size_t)p + 2] - cz) * scale;
                 const float nrm = sqrtf(x * x + y * y + z * z);
                 const float amax = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
                 const float stretch = amax < 1e-8f ? 0.f : 0.5f * nrm / amax;
                 x = fminf(fmaxf((x * stretch + ox + 0.5f) * sm1, 0.f), sm1);
                 y = fminf(fmaxf((y * stretch + oy + 0.5f) * sm1, 0.f), sm1);
                 z = fminf(fmaxf((z * stretch + oz + 0.5f) * sm1, 0.f), sm1);
+                const int x0 = min((int)x, S - 1), y0 = min((int)y, S - 1), z0 = min((int)z, S - 1);
+                ax = x - (float)x0;
+                ay = y - (float)y0;
+                az = z - (float)z0;
+                cellinfo = ((z0 * S + y0) * S + x0) | ((x0 == S - 1) << 8) | ((y0 == S - 1) << 9) | ((z0 == S - 1) << 10);
                 f.x *= imp;
                 f.y *= imp;
                 f.z *= imp;
@@ -192,21 +203,21 @@ cconv4_kernel(const float* __restrict__ filters, const float* __restrict__ out_p
             }
             // sum of the neighbour importances, in list order like the reference
             for (int j = 0; j < cnt; ++j) norm += __shfl_sync(0xffffffffu, nimp_l, j);
+            // the per-neighbour records go through a small per-warp staging area: phase B then needs two
+            // broadcast loads per neighbour instead of eight shuffles
+            __syncwarp();
+            reinterpret_cast<float4*>(stage)[2 * lane] = make_float4(__int_as_float(cellinfo), ax, ay, az);
+            reinterpret_cast<float4*>(stage)[2 * lane + 1] = f;
+            __syncwarp();
             // ---- phase B: lane = tap x channel
             for (int j = 0; j < cnt; ++j) {
-                const float xj = __shfl_sync(0xffffffffu, x, j), yj = __shfl_sync(0xffffffffu, y, j),
-                            zj = __shfl_sync(0xffffffffu, z, j);
-                const float f0 = __shfl_sync(0xffffffffu, f.x, j), f1 = __shfl_sync(0xffffffffu, f.y, j),
-                            f2 = __shfl_sync(0xffffffffu, f.z, j), f3 = __shfl_sync(0xffffffffu, f.w, j);
-                const float fj = ch == 0 ? f0 : ch == 1 ? f1 : ch == 2 ? f2 : f3;
-                const int x0 = min((int)xj, S - 1), y0 = min((int)yj, S - 1), z0 = min((int)zj, S - 1);
-                const float ax = xj - (float)x0, ay = yj - (float)y0, az = zj - (float)z0;
+                const float4 rec = reinterpret_cast<const float4*>(stage)[2 * j];
+                const float fj = stage[8 * j + 4 + ch];
+                const int ci = __float_as_int(rec.x);
                 // a "+1" tap that is clamped onto its "+0" twin carries weight 0: skip
-                const bool dup = (tx && x0 == S - 1) || (ty && y0 == S - 1) || (tz && z0 == S - 1);
-                if (!dup) {
-                    const float w = (tx ? ax : 1.f - ax) * (ty ? ay : 1.f - ay) * (tz ? az : 1.f - az);
-                    const int cell = ((z0 + tz) * S + (y0 + ty)) * S + (x0 + tx);
-                    B[cell * 4 + ch] += w * fj;
+                if (!(ci & tapmask)) {
+                    const float w = (tx ? rec.y : 1.f - rec.y) * (ty ? rec.z : 1.f - rec.z) * (tz ? rec.w : 1.f - rec.w);
+                    B[((ci & 0xff) + tapoff) * 4 + ch] += w * fj;
                 }
                 __syncwarp();
             }
@@ -239,7 +250,7 @@ void continuous_conv(const float* filters, const float* out_pos, const float* ex
                      int normalize, const float* bias, int relu, float* out, cudaStream_t s) {
     if (V == 0) return;
     if (Cin == 4 && S == 4 && ((uintptr_t)inp_feat % 16) == 0) {
-        const size_t smem4 = (size_t)(64 * 4 * Cout + kCc4Warps * kCcGroup * 64 * 4) * sizeof(float);
+        const size_t smem4 = (size_t)(64 * 4 * Cout + kCc4Warps * kCcGroup * 64 * 4 + kCc4Warps * 256) * sizeof(float);
         if (smem4 <= 160 * 1024) {
             ASRB_CUDA(cudaFuncSetAttribute(cconv4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
             const unsigned blocks = (unsigned)std::min<size_t>(grid_for(V, kCc4Warps), 148 * 2);
