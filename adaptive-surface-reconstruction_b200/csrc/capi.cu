@@ -101,6 +101,7 @@ int asr_set_option(const char* name, int value) {
             sparse_conv_pm_debug(value);
             sparse_conv_os_debug(value);
         }
+        else if (std::string(name) == "conv_row_block_shift") sparse_conv_row_block_shift(value);
         else if (std::string(name) == "tc_ntile") sparse_conv_tc_ntile(value);
         else if (std::string(name) == "tc_stages") sparse_conv_tc_tune(value, 0);
         else if (std::string(name) == "tc_row_groups") sparse_conv_tc_tune(0, value);

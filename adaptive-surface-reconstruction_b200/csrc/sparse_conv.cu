@@ -48,14 +48,16 @@ constexpr int kThreads = 256;  // 16 x 16
 // Morton-ordered within a level) and, inside a block, sorted stably by slot.  A
 // block's gathers and reductions then stay L2-resident while its <=55 slot runs
 // are processed, and W[slot] is still reused by whole 128-pair tiles.
-constexpr int kRowBlockShift = 15;
+static int g_row_block_shift = 15;  // dev knob: option conv_row_block_shift
+void sparse_conv_row_block_shift(int v) { g_row_block_shift = std::max(10, std::min(v, 24)); }
+#define kRowBlockShift g_row_block_shift
 
 // Sort key of an entry: slot-0 entries first (bit `kb`), then (row block, slot).  With the self
 // slot first, and every row owning exactly one slot-0 entry (all within-grid tables), the
 // slot-0 tiles can STORE their rows — that initialises the whole output, so neither a zero
 // fill nor reductions are needed for 1/8 of the pairs (sparse_conv_forward).
 __global__ void __launch_bounds__(256)
-entry_rows_kernel(const int64_t* __restrict__ splits, long long V, const uint8_t* __restrict__ slot, int kb,
+entry_rows_kernel(const int64_t* __restrict__ splits, long long V, const uint8_t* __restrict__ slot, int kb, int rbs,
                   uint32_t* __restrict__ rows, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                   int* __restrict__ not_one_slot0) {
     const long long v = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3;
@@ -63,7 +65,7 @@ entry_rows_kernel(const int64_t* __restrict__ splits, long long V, const uint8_t
     int n0 = 0;
     if (v < V) {
         const int64_t e = splits[v + 1];
-        const uint32_t hi = (uint32_t)(v >> kRowBlockShift) << 8;
+        const uint32_t hi = (uint32_t)(v >> rbs) << 8;
         for (int64_t j = splits[v] + sub; j < e; j += 8) {
             const uint32_t k = slot[j];
             rows[j] = (uint32_t)v;
@@ -195,7 +197,7 @@ void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, c
     DevBuf<int> flag(1, s);
     ASRB_CUDA(cudaMemsetAsync(flag.get(), 0, sizeof(int), s));
     if (E) {
-        entry_rows_kernel<<<grid_for((size_t)V_out * 8, 256), 256, 0, s>>>(d_splits, V_out, d_slot, bits, rows.get(),
+        entry_rows_kernel<<<grid_for((size_t)V_out * 8, 256), 256, 0, s>>>(d_splits, V_out, d_slot, bits, kRowBlockShift, rows.get(),
                                                                           keys.get(), P.perm.get(), flag.get());
         ASRB_CHECK_LAUNCH();
         sort_pairs_u32_u32(keys.get(), P.perm.get(), (size_t)E, s, bits + 1);

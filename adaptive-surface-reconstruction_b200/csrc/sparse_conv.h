@@ -77,6 +77,7 @@ void sparse_conv_pm_tiles(const ConvPlan& P, const float* x, const float* wp, in
 
 // output-stationary persistent tensor-core path; see sparse_conv_os.cu
 void sparse_conv_tc_tune(int stages, int mt);
+void sparse_conv_row_block_shift(int v);
 void sparse_conv_tc_ntile(int n);
 int sparse_conv_tc_row_groups();
 void sparse_conv_os_enable(bool on);

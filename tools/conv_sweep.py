@@ -30,6 +30,10 @@ def run(label, **opts):
           ", ".join("%s=%.1f" % (k.split("/")[1], m) for m, k in top)), flush=True)
 run("stages=2 mt=1", tc_stages=2, tc_row_groups=1)
 if len(sys.argv) > 2 and sys.argv[2] == "one": sys.exit(0)
+if len(sys.argv) > 2 and sys.argv[2] == "rbs":
+    for v in (14, 16, 17, 18):
+        run("row block 2^%d" % v, conv_row_block_shift=v)
+    sys.exit(0)
 if len(sys.argv) > 2 and sys.argv[2] == "os":
     run("hybrid os", sparse_conv_output_stationary=1)
     sys.exit(0)
