@@ -48,7 +48,6 @@ class ShardedPlan:
         self.range = rng              # (a, b, n)
         self.entry_range = entry_range
         self.replicated = replicated
-        self.need = None              # sorted unique input rows this rank's share of the table reads
         self.halo = {}                # input row count -> exchange lists (ShardedOps._halo_lists)
 
 
@@ -104,16 +103,18 @@ class ShardedOps:
         if lists is not None:
             return lists
         ia, ib, n_in = row_range(num_in, self.rank, self.world)
-        if plan.need is None:
-            e0, e1 = plan.entry_range
-            plan.need = torch.unique(plan.idx[e0:e1].long())
-        remote = plan.need[(plan.need < ia) | (plan.need >= ib)]
+        # rows my share of the table reads and somebody else owns: a mark array instead of a sort
+        e0, e1 = plan.entry_range
+        mark = torch.zeros(num_in, dtype=torch.bool, device=plan.idx.device)
+        mark[plan.idx[e0:e1].long()] = True
+        mark[ia:ib] = False
+        remote = torch.nonzero(mark).reshape(-1)  # ascending, hence grouped by owner
         owner = torch.div(remote, n_in, rounding_mode="floor")
         want = torch.bincount(owner, minlength=self.world)[:self.world]  # rows I want from each rank
         table = torch.empty((self.world, self.world), dtype=torch.int64, device=want.device)
         dist.all_gather_into_tensor(table.reshape(-1), want.contiguous(), group=self.group)
         want_l, give_l = want.tolist(), table[:, self.rank].tolist()  # give_l[r] = rows rank r wants from me
-        recv_idx = remote  # ascending, hence grouped by owner
+        recv_idx = remote
         send_idx = torch.empty(int(sum(give_l)), dtype=torch.int64, device=want.device)
         ops, o_r, o_s = [], 0, 0
         for r in range(self.world):
