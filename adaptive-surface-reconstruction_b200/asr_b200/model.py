@@ -176,6 +176,8 @@ class UNet(torch.nn.Module):
             return cache
         L = self.octree_levels
         d, K = input_dict, self.K
+        if hasattr(K, "prepare"):  # multi-GPU: row ownership of the coarser grid levels
+            K.prepare(d, L)
         P = {"nb": [], "up": [], "down": []}
         for i in range(L):
             P["nb"].append(K.ConvPlan(d["neighbors_index%d" % i], d["neighbors_kernel_index%d" % i],

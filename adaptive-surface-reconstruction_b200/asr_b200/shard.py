@@ -277,3 +277,333 @@ class ShardedOps:
                              signed_scale=None if signed_scale is None else signed_scale[a:b].contiguous())
         full[self.rank * n:self.rank * n + (b - a)] = v
         return self._gather_rows(full, V, n)
+
+
+# =====================================================================================
+# Spatial ownership: the same decomposition with rows assigned by REGION instead of by index range.
+#
+# The rows of a grid are ordered by location code = octree level first, then Morton (the
+# reference's order), so an index range [a, b) is "all coarse voxels plus a slice of the fine
+# ones" and ~14 % of the rows a rank reads belong to somebody else.  Here the domain is cut along
+# the Z-curve into `world` regions of equal level-0 voxel count, and on every grid level a rank
+# owns, inside each octree-level segment of the row list, the (contiguous) rows of its region.
+# Coarse and fine voxels of one place then live on the same rank and only the voxels along the
+# region borders are exchanged.  Ownership is a few index ranges per level, so the local tables
+# are concatenations of slices and the outputs go back with a few block copies.
+def _morton10(q):
+    """interleave the low 10 bits of the three integer columns of q [n, 3] (x lowest)"""
+    def spread(v):
+        v = v & 0x3FF
+        v = (v | (v << 16)) & 0x030000FF
+        v = (v | (v << 8)) & 0x0300F00F
+        v = (v | (v << 4)) & 0x030C30C3
+        v = (v | (v << 2)) & 0x09249249
+        return v
+    return spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+
+
+class _Ownership:
+    """rows of one grid level owned by this rank: `ranges` [(lo, hi)], `rows` (ascending), and
+    `owner` [V] = rank of every row."""
+
+    def __init__(self, V, bounds, rank, device):
+        # bounds: list over octree-level segments of a list of world + 1 row indices
+        self.V = V
+        self.ranges = [(b[rank], b[rank + 1]) for b in bounds if b[rank + 1] > b[rank]]
+        self.owner = torch.empty(V, dtype=torch.int64, device=device)
+        for b in bounds:
+            for r in range(len(b) - 1):
+                if b[r + 1] > b[r]:
+                    self.owner[b[r]:b[r + 1]] = r
+        self.rows = (torch.cat([torch.arange(lo, hi, device=device) for lo, hi in self.ranges])
+                     if self.ranges else torch.empty(0, dtype=torch.int64, device=device))
+        self.n = int(self.rows.shape[0])
+
+    def take(self, t):
+        """rows of `t` owned by this rank, in order"""
+        if len(self.ranges) == 1:
+            lo, hi = self.ranges[0]
+            return t[lo:hi].contiguous()
+        return torch.cat([t[lo:hi] for lo, hi in self.ranges]) if self.ranges else t[:0].contiguous()
+
+    def put(self, full, local):
+        o = 0
+        for lo, hi in self.ranges:
+            full[lo:hi] = local[o:o + hi - lo]
+            o += hi - lo
+        return full
+
+
+class _SpatialPlan:
+    def __init__(self, base_plan, idx, row_splits, own, entry_slices, replicated):
+        self.base = base_plan
+        self.idx = idx                # full neighbour index (importance gather)
+        self.row_splits = row_splits  # full row splits
+        self.num_out = row_splits.shape[0] - 1
+        self.own = own
+        self.entry_slices = entry_slices
+        self.replicated = replicated
+        self.local_idx = None
+        self.halo = {}
+
+
+class SpatialShardedOps:
+
+    def __init__(self, base, group=None, min_rows=16384):
+        self.base = base
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.min_rows = min_rows
+        self.collectives = 0
+        self.bytes_gathered = 0
+        self._own = {}        # row count of a grid level -> _Ownership
+        self._frame = None    # (lo, scale, thresholds) of the region cut
+        self._agg = None      # (ownership of level 0, local row splits of the aggregation lists)
+
+    def __getattr__(self, name):
+        return getattr(self.base, name)
+
+    # ------------------------------------------------------------------ ownership
+    def _codes(self, centers):
+        lo, scale, _ = self._frame
+        q = ((centers - lo) * scale).clamp_(0, 1023).long()
+        return _morton10(q)
+
+    def _make_ownership(self, centers, sizes):
+        V = centers.shape[0]
+        change = torch.nonzero(sizes[1:] != sizes[:-1]).reshape(-1) + 1
+        seg = [0] + change.tolist() + [V]
+        thresholds = self._frame[2]
+        codes = self._codes(centers)
+        bounds = []
+        for s0, s1 in zip(seg[:-1], seg[1:]):
+            cm = torch.cummax(codes[s0:s1], 0).values  # monotone even if the frames are not aligned
+            cut = (torch.searchsorted(cm, thresholds) + s0).tolist()
+            bounds.append([s0] + cut + [s1])
+        return _Ownership(V, bounds, self.rank, centers.device)
+
+    def _level0(self, centers, sizes):
+        """region cut (once per cloud) and the ownership of the finest grid"""
+        lo = centers.min(0).values
+        ext = (centers.max(0).values - lo).max().clamp_min(1e-30)
+        self._frame = (lo, 1023.0 / ext, None)
+        codes = torch.sort(self._codes(centers)).values
+        V = codes.shape[0]
+        cut = torch.tensor([(k * V) // self.world for k in range(1, self.world)], dtype=torch.int64, device=codes.device)
+        self._frame = (lo, 1023.0 / ext, codes[cut].contiguous())
+        self._own = {V: self._make_ownership(centers, sizes)}
+        return self._own[V]
+
+    def prepare(self, input_dict, levels):
+        """ownership of the coarser grid levels (called by model.plans before the plans are built)"""
+        for l in range(1, levels):
+            c = input_dict.get("voxel_centers%d" % l)
+            if c is None or self._frame is None or c.shape[0] < self.min_rows or self.world == 1:
+                continue
+            if c.shape[0] not in self._own:
+                self._own[c.shape[0]] = self._make_ownership(c, input_dict["voxel_sizes%d" % l])
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _tag(t, V):
+        t._asr_rows = V
+        return t
+
+    def _all_reduce(self, t):
+        dist.all_reduce(t, group=self.group)
+        self.collectives += 1
+        self.bytes_gathered += t.numel() * t.element_size()
+        return t
+
+    def _make_full(self, x):
+        V = getattr(x, "_asr_rows", None)
+        if V is None:
+            return x
+        own = self._own[V]
+        full = torch.zeros_like(x)
+        own.put(full, own.take(x))
+        return self._all_reduce(full)
+
+    def _halo_lists(self, plan, x_rows):
+        lists = plan.halo.get(x_rows)
+        if lists is not None:
+            return lists
+        own_in = self._own[x_rows]
+        mark = torch.zeros(x_rows, dtype=torch.bool, device=plan.idx.device)
+        mark[plan.local_idx.long()] = True
+        for lo, hi in own_in.ranges:
+            mark[lo:hi] = False
+        remote = torch.nonzero(mark).reshape(-1)
+        owner = own_in.owner[remote]
+        order = torch.sort(owner, stable=True).indices
+        remote, owner = remote[order], owner[order]
+        want = torch.bincount(owner, minlength=self.world)[:self.world]
+        table = torch.empty((self.world, self.world), dtype=torch.int64, device=want.device)
+        dist.all_gather_into_tensor(table.reshape(-1), want.contiguous(), group=self.group)
+        want_l, give_l = want.tolist(), table[:, self.rank].tolist()
+        send_idx = torch.empty(int(sum(give_l)), dtype=torch.int64, device=want.device)
+        ops, o_r, o_s = [], 0, 0
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            if want_l[r]:
+                ops.append(dist.P2POp(dist.isend, remote[o_r:o_r + want_l[r]].contiguous(), r, self.group))
+            if give_l[r]:
+                ops.append(dist.P2POp(dist.irecv, send_idx[o_s:o_s + give_l[r]], r, self.group))
+            o_r += want_l[r]
+            o_s += give_l[r]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        lists = (send_idx, give_l, remote, want_l)
+        plan.halo[x_rows] = lists
+        self.collectives += 1
+        return lists
+
+    def _fetch_halo(self, plan, x):
+        V = getattr(x, "_asr_rows", None)
+        if V is None:
+            return x
+        send_idx, give_l, recv_idx, want_l = self._halo_lists(plan, V)
+        send = x.index_select(0, send_idx)
+        recv = torch.empty((recv_idx.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        ops, o_r, o_s = [], 0, 0
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            if give_l[r]:
+                ops.append(dist.P2POp(dist.isend, send[o_s:o_s + give_l[r]], r, self.group))
+            if want_l[r]:
+                ops.append(dist.P2POp(dist.irecv, recv[o_r:o_r + want_l[r]], r, self.group))
+            o_r += want_l[r]
+            o_s += give_l[r]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            x.index_copy_(0, recv_idx, recv)
+            self.collectives += 1
+            self.bytes_gathered += recv.numel() * recv.element_size()
+        return x
+
+    def cat(self, tensors, dim=-1):
+        out = torch.cat(tensors, dim)
+        tags = [getattr(t, "_asr_rows", None) for t in tensors]
+        tag = next((t for t in tags if t is not None), None)
+        return self._tag(out, tag) if tag is not None else out
+
+    def add(self, x, y):
+        out = x + y
+        tag = getattr(x, "_asr_rows", None) or getattr(y, "_asr_rows", None)
+        return self._tag(out, tag) if tag is not None else out
+
+    # ------------------------------------------------------------------ sparse convolution
+    def ConvPlan(self, neighbors_index, neighbors_kernel_index, neighbors_row_splits, kernel_size):
+        V = neighbors_row_splits.shape[0] - 1
+        own = self._own.get(V) if self.world > 1 else None
+        if own is None:
+            p = self.base.ConvPlan(neighbors_index, neighbors_kernel_index, neighbors_row_splits, kernel_size)
+            return _SpatialPlan(p, neighbors_index, neighbors_row_splits, None, None, True)
+        rs = neighbors_row_splits
+        ends = rs[torch.tensor([v for r in own.ranges for v in r], dtype=torch.int64, device=rs.device)].tolist()
+        slices = list(zip(ends[0::2], ends[1::2]))
+        idx = torch.cat([neighbors_index[a:b] for a, b in slices]) if slices else neighbors_index[:0]
+        slot = torch.cat([neighbors_kernel_index[a:b] for a, b in slices]) if slices else neighbors_kernel_index[:0]
+        parts, off = [], 0
+        for (lo, hi), (a, b) in zip(own.ranges, slices):
+            parts.append(rs[lo:hi] - a + off)
+            off += b - a
+        parts.append(torch.tensor([off], dtype=rs.dtype, device=rs.device))
+        p = self.base.ConvPlan(idx.contiguous(), slot.contiguous(), torch.cat(parts).contiguous(), kernel_size)
+        plan = _SpatialPlan(p, neighbors_index, neighbors_row_splits, own, slices, False)
+        plan.local_idx = idx
+        return plan
+
+    def sparse_conv(self, plan, filters, inp_features, inp_importance=None, neighbors_importance=None,
+                    importance_col=0, normalize=False, normalize_col=0, normalizer=None, bias=None, relu=False,
+                    **kw):
+        if plan.replicated:
+            inp_features = self._make_full(inp_features)
+            return self.base.sparse_conv(plan.base, filters, inp_features, inp_importance=inp_importance,
+                                         neighbors_importance=neighbors_importance, importance_col=importance_col,
+                                         normalize=normalize, normalize_col=normalize_col, normalizer=normalizer,
+                                         bias=bias, relu=relu, **kw)
+        own = plan.own
+        cout = filters.shape[2]
+        inp_features = self._fetch_halo(plan, inp_features)
+        nimp = None
+        if neighbors_importance is not None:
+            nimp = torch.cat([neighbors_importance[a:b] for a, b in plan.entry_slices])
+        local = torch.empty((own.n, cout), dtype=torch.float32, device=inp_features.device)
+        res = self.base.sparse_conv(plan.base, filters, inp_features, inp_importance=inp_importance,
+                                    neighbors_importance=nimp, importance_col=importance_col, normalize=normalize,
+                                    normalize_col=normalize_col,
+                                    normalizer=None if normalizer is None else own.take(normalizer), bias=bias,
+                                    relu=relu, out=local, **kw)
+        full = torch.empty((plan.num_out, cout), dtype=torch.float32, device=inp_features.device)
+        own.put(full, res)
+        return self._tag(full, own.V)
+
+    # ------------------------------------------------------------------ aggregation
+    def multi_radius_search(self, points, queries, radii, frame=None):
+        V = queries.shape[0]
+        self._own, self._frame, self._agg = {}, None, None
+        if self.world == 1 or V < self.min_rows:
+            return self.base.multi_radius_search(points, queries, radii, frame=frame)
+        own = self._level0(queries, radii)
+        idx, dist2, rs = self.base.multi_radius_search(points, own.take(queries), own.take(radii), frame=frame)
+        self._agg = (own, rs)
+        return idx, dist2, rs
+
+    def scale_compatibility(self, voxel_sizes, point_radii, neighbors_index, neighbors_row_splits):
+        if self._agg is not None:
+            voxel_sizes = self._agg[0].take(voxel_sizes)
+        return self.base.scale_compatibility(voxel_sizes, point_radii, neighbors_index, neighbors_row_splits)
+
+    def continuous_conv(self, filters, out_positions, extents, offset, inp_positions, inp_features, inp_importance,
+                        neighbors_index, neighbors_importance, neighbors_row_splits, normalize=True, bias=None,
+                        relu=False):
+        if self._agg is None:
+            return self.base.continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_features,
+                                             inp_importance, neighbors_index, neighbors_importance,
+                                             neighbors_row_splits, normalize=normalize, bias=bias, relu=relu)
+        own = self._agg[0]
+        local = self.base.continuous_conv(filters, own.take(out_positions), own.take(extents), offset, inp_positions,
+                                          inp_features, inp_importance, neighbors_index, neighbors_importance,
+                                          neighbors_row_splits, normalize=normalize, bias=bias, relu=relu)
+        full = torch.empty((own.V, local.shape[1]), dtype=local.dtype, device=local.device)
+        own.put(full, local)
+        return self._tag(full, own.V)
+
+    def pair_importance_for_unet(self, importance, num_voxels):
+        """First `num_voxels` entries of the GLOBAL (row-ordered) pair-importance list, the only
+        ones the first encoder block reads."""
+        if self._agg is None:
+            return importance
+        own, rs = self._agg
+        cnt = rs[1:] - rs[:-1]
+        counts = torch.zeros(own.V, dtype=torch.int64, device=importance.device)
+        counts[own.rows] = cnt
+        self._all_reduce(counts)
+        total = int(counts.sum().item())
+        if total < num_voxels:
+            raise IndexError("fewer aggregation pairs (%d) than voxels (%d)" % (total, num_voxels))
+        start = (torch.cumsum(counts, 0) - counts)[own.rows]  # global position of each local row's first pair
+        gpos = torch.repeat_interleave(start - rs[:-1], cnt) + torch.arange(importance.shape[0], device=importance.device)
+        first = torch.zeros(num_voxels, dtype=torch.float32, device=importance.device)
+        m = gpos < num_voxels
+        first[gpos[m]] = importance[m]
+        return self._all_reduce(first)
+
+    # ------------------------------------------------------------------ decoder
+    def decode(self, shifts, code, *weights, signed_scale=None, with_gradient=False):
+        V = getattr(code, "_asr_rows", None)
+        if with_gradient or V is None:
+            code = self._make_full(code)
+            return self.base.decode(shifts, code, *weights, signed_scale=signed_scale, with_gradient=with_gradient)
+        own = self._own[V]
+        v = self.base.decode(None if shifts is None else own.take(shifts), own.take(code), *weights,
+                             signed_scale=None if signed_scale is None else own.take(signed_scale))
+        full = torch.zeros((V, 2), dtype=torch.float32, device=code.device)
+        own.put(full, v)
+        return self._all_reduce(full)

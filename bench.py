@@ -203,7 +203,8 @@ def run_gpu(args):
     cloud = clouds.make(args.workload, args.points, seed=args.seed)
     net = model.seeded_weights(model.UNet(args.levels), seed=0).cuda()
     if world > 1:
-        net.K = shard.ShardedOps(ops)
+        # rows owned by spatial region (default) or by contiguous index range (ASR_SHARD=range)
+        net.K = (shard.ShardedOps if os.environ.get("ASR_SHARD") == "range" else shard.SpatialShardedOps)(ops)
     host = {k: torch.from_numpy(cloud[k]).pin_memory() for k in ("points", "normals", "radii")}
     devt = {k: v.cuda() for k, v in host.items()}
     bb = (cloud["bb_min"], cloud["bb_max"])
@@ -325,7 +326,7 @@ def run_gpu(args):
             "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f32 (3xTF32 on tcgen05 for the sparse convs)" if ops.SPARSE_CONV_BACKEND == "tensor" else "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(args), "sparse_conv_backend": ops.SPARSE_CONV_BACKEND, "parallelism": ("%d gpus: geometry replicated, search/conv/decode sharded by output-voxel ranges, "
+            "config": {"workload": workload_name(args), "sparse_conv_backend": ops.SPARSE_CONV_BACKEND, "parallelism": ("%d gpus: geometry replicated, search/conv/decode sharded by spatial region (Z-curve cut), "
                                        "peer-to-peer halo-row exchange before each sharded conv (%d exchanges, %.3f GB "
                                        "received per rank and step)"
                                        % (world, net.K.collectives // max(total_steps, 1),

@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(rank, world, port, q):
+def _run(rank, world, port, q, kind="ShardedOps"):
     for p in (ROOT, os.path.join(ROOT, "adaptive-surface-reconstruction_b200"), os.path.join(ROOT, "tests")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -28,29 +28,35 @@ def _run(rank, world, port, q):
         net = model.seeded_weights(model.UNet(3), seed=1)
         net.K = cpu_ops
         ref = pipeline.reconstruct_vertices(net, pts, nrm, rad, c["bb_min"], c["bb_max"], contouring_value_threshold=1e9)
-        K = shard.ShardedOps(cpu_ops, min_rows=64)
+        K = getattr(shard, kind)(cpu_ops, min_rows=64)
         net.K = K
         out = pipeline.reconstruct_vertices(net, pts, nrm, rad, c["bb_min"], c["bb_max"], contouring_value_threshold=1e9)
         err = float((out["values"] - ref["values"]).abs().max())
         same_v = bool(torch.equal(out["vertex_dual"], ref["vertex_dual"]))
         verr = float((out["vertices"] - ref["vertices"]).abs().max()) if same_v and out["vertices"].numel() else 0.0
         # the aggregation arrays are this rank's share of the global lists
-        a, b, n = shard.row_range(ref["values"].shape[0], rank, world)
         rs_ref = ref["input_dict"]["aggregation_row_splits"]
         rs_loc = out["input_dict"]["aggregation_row_splits"]
-        share_ok = bool(torch.equal(rs_loc, rs_ref[a:b + 1] - rs_ref[a]))
+        if kind == "ShardedOps":
+            a, b, n = shard.row_range(ref["values"].shape[0], rank, world)
+            share_ok = bool(torch.equal(rs_loc, rs_ref[a:b + 1] - rs_ref[a]))
+        else:  # this rank's rows are a few index ranges: the local list holds exactly their pair counts
+            rows = K._agg[0].rows
+            share_ok = bool(torch.equal(rs_loc[1:] - rs_loc[:-1], (rs_ref[1:] - rs_ref[:-1])[rows])) and \
+                0 < rows.shape[0] < ref["values"].shape[0]
         q.put((rank, err, same_v, verr, K.collectives, share_ok, int(ref["values"].shape[0]),
                float(ref["values"].abs().max())))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_pipeline_matches_single_process(world):
+@pytest.mark.parametrize("world,kind", [(2, "ShardedOps"), (3, "ShardedOps"), (2, "SpatialShardedOps"),
+                                        (3, "SpatialShardedOps")])
+def test_sharded_pipeline_matches_single_process(world, kind):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 400) + world
-    procs = [ctx.Process(target=_run, args=(r, world, port, q)) for r in range(world)]
+    port = 29500 + (os.getpid() % 400) + world + (10 if kind != "ShardedOps" else 0)
+    procs = [ctx.Process(target=_run, args=(r, world, port, q, kind)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in range(world)]
