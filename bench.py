@@ -203,8 +203,9 @@ def run_gpu(args):
     cloud = clouds.make(args.workload, args.points, seed=args.seed)
     net = model.seeded_weights(model.UNet(args.levels), seed=0).cuda()
     if world > 1:
-        # rows owned by spatial region (default) or by contiguous index range (ASR_SHARD=range)
-        net.K = (shard.ShardedOps if os.environ.get("ASR_SHARD") == "range" else shard.SpatialShardedOps)(ops)
+        # rows owned by contiguous index range (default) or by spatial region (ASR_SHARD=spatial: 19x
+        # less halo traffic, but its torch-level bookkeeping still costs more than it saves)
+        net.K = (shard.SpatialShardedOps if os.environ.get("ASR_SHARD") == "spatial" else shard.ShardedOps)(ops)
     host = {k: torch.from_numpy(cloud[k]).pin_memory() for k in ("points", "normals", "radii")}
     devt = {k: v.cuda() for k, v in host.items()}
     bb = (cloud["bb_min"], cloud["bb_max"])
@@ -326,10 +327,11 @@ def run_gpu(args):
             "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f32 (3xTF32 on tcgen05 for the sparse convs)" if ops.SPARSE_CONV_BACKEND == "tensor" else "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(args), "sparse_conv_backend": ops.SPARSE_CONV_BACKEND, "parallelism": ("%d gpus: geometry replicated, search/conv/decode sharded by spatial region (Z-curve cut), "
+            "config": {"workload": workload_name(args), "sparse_conv_backend": ops.SPARSE_CONV_BACKEND, "parallelism": ("%d gpus: geometry replicated, search/conv/decode sharded by %s, "
                                        "peer-to-peer halo-row exchange before each sharded conv (%d exchanges, %.3f GB "
                                        "received per rank and step)"
-                                       % (world, net.K.collectives // max(total_steps, 1),
+                                       % (world, "spatial region (Z-curve cut)" if isinstance(net.K, shard.SpatialShardedOps)
+                                          else "output-voxel index ranges", net.K.collectives // max(total_steps, 1),
                                           net.K.bytes_gathered / max(total_steps, 1) / 1e9)) if world > 1 else "1 gpu",
                        "l2_policy": "inputs and every intermediate tensor larger than the 126 MB L2",
                        "sizes": sizes},
