@@ -246,7 +246,8 @@ def run_gpu(args):
     # ---- device-resident timing (value) with the kernel profiler on
     barrier()
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:  # one nvidia-smi poller per box: several of them stall the driver for 100s of ms (seen at N = 2)
+        sampler.start()
     _lib.profile_reset()
     _lib.profile_enable(True)
     launches0 = _lib.kernel_launches()
