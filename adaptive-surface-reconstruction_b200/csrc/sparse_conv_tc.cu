@@ -14,17 +14,22 @@
 //
 // Warp-specialised, mbarrier pipeline of up to 4 stages of 16 input channels:
 //   * producers (warps 0-3): 4 lanes fetch one 64-byte row chunk (coalesced), keep
-//     4 chunks in flight in registers, split into hi/lo and store into the
-//     K-major no-swizzle canonical layout (LBO = 144 B so the 16-byte stores of a
-//     warp spread evenly over the banks), fence.proxy.async, arrive on `full`.
+//     2-4 chunks in flight in registers, split into hi/lo and store into the
+//     K-major no-swizzle canonical layout (8-row groups dense, the four 16-byte
+//     column planes 16 * 128 + 32 bytes apart: a quarter-warp's 16-byte stores hit
+//     all 32 banks once, umma.cuh), fence.proxy.async, arrive on `full`.
 //   * B (W[slot] chunk, hi and lo): pre-packed once per filter bank in the
 //     canonical layout; one `cp.async.bulk` (1-D TMA) per chunk completing its
 //     bytes on the same `full` barrier.
-//   * MMA issuer (one lane of warp 4): waits `full`, issues the 6 MMAs of the
-//     chunk, tcgen05.commit -> `empty` (stage reusable); a last commit -> `acc`.
+//   * MMA issuer (one lane of warp 4): waits `full`, issues the 4 MMAs of the
+//     chunk — A_hi x [B_hi | B_lo] as ONE MMA of width 2 N (the lo rows follow the
+//     hi rows in the stage, the correction accumulator follows the main one in
+//     TMEM) and A_lo x B_hi — tcgen05.commit -> `empty`; a last commit -> `acc`.
 //   * epilogue (warps 0-3 again): tcgen05.ld (thread = pair = TMEM lane), main +
-//     correction, per-row importance on the weighted channels,
-//     red.global.add.v4.f32 scatter into the output rows.
+//     correction, per-row importance on the weighted channels, the pair's output
+//     segment staged in shared memory and added to its output row by ONE bulk
+//     reduction (cp.reduce.async.bulk.add.f32, TMA engine) — or bulk-STORED for
+//     the slot-0 tiles, which come first in the tile list and initialise the output.
 #include "internal.h"
 #include "profile.cuh"
 #include "sparse_conv.h"
