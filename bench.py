@@ -320,6 +320,12 @@ def run_gpu(args):
             "hbm_roofline_frac": total_bytes / (peaks["hbm_gbs"] * 1e9) * 1e3 / ms_step,
             "bytes_by_stage": bytes_by_stage,
         }
+        # algorithmic GB/s per stage (host-synchronised stage times of the last warm-up step)
+        stage_of = {"octree_keys": "octree", "neighbor_tables": "grids", "duals": "duals", "search": "search",
+                    "continuous_conv": "aggregate", "sparse_conv_stack": "unet", "decode": "decode", "contour": "contour"}
+        path["achieved_gbs_by_stage"] = {k: round(b / (stage_ms[stage_of[k]] * 1e-3) / 1e9, 1)
+                                         for k, b in bytes_by_stage.items() if stage_ms.get(stage_of[k], 0) > 0}
+        path["hbm_peak_gbs"] = peaks["hbm_gbs"]
         kernels = {k: {"ms_per_step": round(v["ms"] / args.steps, 4), "launches_per_step": v["launches"] // args.steps}
                    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
         line = {
