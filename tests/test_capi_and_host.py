@@ -167,3 +167,25 @@ def test_ply_reader_and_writer(tmp_path):
     plyio.write_mesh(str(m), pts, tri)
     v, t = plyio.read_mesh(str(m))
     assert np.array_equal(v, pts) and np.array_equal(t, tri)
+
+
+def test_bench_byte_model_matches_the_survey_formulas():
+    """bench.py's algorithmic byte model on a hand-checked configuration."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    sizes = {"N": 1000, "V": [100, 20], "E": [700, 120], "P": 1500, "D": 60, "M": 30}
+    convs = [{"V_in": 100, "V_out": 100, "E": 700, "K": 55, "Cin": 32, "Cout": 64, "importance": True},
+             {"V_in": 100, "V_out": 20, "E": 100, "K": 9, "Cin": 64, "Cout": 128, "importance": False}]
+    got = b.algorithmic_bytes(sizes, convs)
+    assert got["octree_keys"] == 16 * 1000 + 8 * 100
+    assert got["neighbor_tables"] == (8 * 100 + 5 * 700 + 8 * 101) + (8 * 20 + 5 * 120 + 8 * 21) + 21 * 100
+    assert got["duals"] == 8 * 100 + 64 * 60
+    assert got["search"] == 12 * 1000 + 16 * 100 + 12 * 1500 + 8 * 101
+    assert got["continuous_conv"] == 12 * 1500 + 8 * 101 + 28 * 1000 + 16 * 100 + 128 * 100 + 4 * 1500
+    c0 = 4 * 100 * 32 + 4 * 100 * 64 + 5 * 700 + 8 * 101 + 4 * 55 * 32 * 64 + 4 * 100 + 4 * 100
+    c1 = 4 * 100 * 64 + 4 * 20 * 128 + 5 * 100 + 8 * 21 + 4 * 9 * 64 * 128
+    assert got["sparse_conv_stack"] == c0 + c1
+    assert got["decode"] == 136 * 100 and got["contour"] == 64 * 60 + 20 * 100 + 12 * 30
+    assert b.conv_traffic_per_launch() is None or b.conv_traffic_per_launch() > 0
