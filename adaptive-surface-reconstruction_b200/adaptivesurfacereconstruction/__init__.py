@@ -92,12 +92,7 @@ def _load_model(levels=5):
     if not os.path.exists(path):
         raise RuntimeError("model.pt not found in the resource dir %r (set ASR_RESOURCE_DIR); the released weights "
                            "are not redistributable offline" % res)
-    try:
-        sd = torch.jit.load(path, map_location="cpu").state_dict()
-    except Exception:
-        sd = torch.load(path, map_location="cpu")
-    sd = {k: v for k, v in sd.items() if not k.startswith("_")}
-    net = _model.from_state_dict(sd, levels)
+    net = _model.from_state_dict(_model.load_weights_file(path), levels)
     _MODEL_CACHE[path] = net
     return net
 

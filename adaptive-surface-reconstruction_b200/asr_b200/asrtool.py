@@ -41,12 +41,7 @@ def main(argv=None):
     if args.random_weights is not None:
         net = _model.seeded_weights(_model.UNet(5), seed=args.random_weights).cuda()
     elif args.model:
-        import torch
-        try:
-            sd = torch.jit.load(args.model, map_location="cpu").state_dict()
-        except Exception:
-            sd = torch.load(args.model, map_location="cpu")
-        net = _model.from_state_dict({k: v for k, v in sd.items() if not k.startswith("_")}, 5)
+        net = _model.from_state_dict(_model.load_weights_file(args.model), 5)
     mesh = asr.reconstruct_surface(points, normals, radii if len(radii) else None, model=net)
     plyio.write_mesh(args.out, mesh["vertices"], mesh["triangles"])
     print("wrote %d vertices, %d triangles to %s" % (len(mesh["vertices"]), len(mesh["triangles"]), args.out))

@@ -191,8 +191,9 @@ class UNet(torch.nn.Module):
         input_dict["_asr_plans"] = P
         return P
 
-    def unet(self, feats1, input_dict):
-        """UNet5.unet (:535-638)."""
+    def unet(self, feats1, input_dict, taps=None):
+        """UNet5.unet (:535-638).  taps: optional dict that receives the encoder output of every
+        level ("enc<l>", the skip tensors) and every decoder block's output ("dec<l>") for parity tests."""
         L, K = self.octree_levels, self.K
         P = self.plans(input_dict)
         x, imp = feats1
@@ -203,10 +204,14 @@ class UNet(torch.nn.Module):
             x, imp = self._down(l).run(x, P["down"][l - 1], imp, K)
             x, imp = getattr(self, "sparseconv_encblock%d" % l).run(x, P["nb"][l], imp, K)
             skips.append(x)
+        if taps is not None:
+            taps.update({"enc%d" % l: s for l, s in enumerate(skips)})
         for l in range(L - 2, -1, -1):
             x, _ = getattr(self, "sparseconv_up%d" % l).run(x, P["up"][l], None, K)
             x = K.cat([x, skips[l]], -1) if l >= 1 else K.add(x, skips[0])
             x, _ = getattr(self, "sparseconv_decblock%d" % l).run(x, P["nb"][l], None, K)
+            if taps is not None:
+                taps["dec%d" % l] = x
         return x
 
     def _decoder(self):
@@ -255,6 +260,31 @@ def seeded_weights(net, seed=0, scaled=True):
                 m._fused = None
                 m._packed = {}
     return net
+
+
+def load_weights_file(path):
+    """Reads the network weights from `path`: a TorchScript archive as written by the reference's
+    models/v0/convert_tf2torchscript.py:117-122 (`model.pt`, loaded by asr.cpp:138-141 with torch::jit::load)
+    or a plain `state_dict` file with the reference's key names.  Returns the state dict.
+
+    The archive's graphs call `open3d::*` ops, so the shim that registers them
+    (open3d.ml.torch.ops of this package) is imported before torch.jit.load — without it the load
+    fails with "Unknown builtin op".  A file that is a zip archive with TorchScript code but fails to
+    load raises that error (it is not retried as a pickle, which would hide the reason)."""
+    import zipfile
+
+    import open3d.ml.torch.ops  # noqa: F401  registers open3d::* (this package's shim, or real Open3D)
+    is_script = False
+    if zipfile.is_zipfile(path):
+        with zipfile.ZipFile(path) as z:
+            is_script = any(n.endswith("constants.pkl") or "/code/" in n for n in z.namelist())
+    if is_script:
+        sd = torch.jit.load(path, map_location="cpu").state_dict()
+    else:
+        sd = torch.load(path, map_location="cpu")
+        if not isinstance(sd, dict):
+            sd = sd.state_dict()
+    return {k: v for k, v in sd.items() if not k.startswith("_")}
 
 
 def from_state_dict(state_dict, levels=5, device="cuda"):

@@ -9,16 +9,23 @@ import torch
 
 from asr_b200 import ops as _k
 
+# Schemas = Open3D v0.14.1's own registrations (cpp/open3d/ml/pytorch/**/*Ops.cpp), INCLUDING the
+# defaulted trailing arguments, so that a TorchScript archive traced against real Open3D
+# (models/v0/convert_tf2torchscript.py:117-122 -> model.pt, loaded by asr.cpp:138-141) resolves its
+# `open3d::*` calls against this library.
 _lib = torch.library.Library("open3d", "DEF")
 _lib.define("invert_neighbors_list(int num_points, Tensor inp_neighbors_index, Tensor inp_neighbors_row_splits, "
-            "Tensor inp_neighbors_attributes) -> (Tensor, Tensor, Tensor)")
+            "Tensor inp_neighbors_attributes) -> (Tensor neighbors_index, Tensor neighbors_row_splits, "
+            "Tensor neighbors_attributes)")
 _lib.define("reduce_subarrays_sum(Tensor values, Tensor row_splits) -> Tensor")
 _lib.define("sparse_conv(Tensor filters, Tensor inp_features, Tensor inp_importance, Tensor neighbors_index, "
             "Tensor neighbors_kernel_index, Tensor neighbors_importance, Tensor neighbors_row_splits, "
-            "bool normalize) -> Tensor")
+            "bool normalize=False, int max_temp_mem_MB=64) -> Tensor")
 _lib.define("continuous_conv(Tensor filters, Tensor out_positions, Tensor extents, Tensor offset, "
             "Tensor inp_positions, Tensor inp_features, Tensor inp_importance, Tensor neighbors_index, "
-            "Tensor neighbors_importance, Tensor neighbors_row_splits, bool normalize) -> Tensor")
+            "Tensor neighbors_importance, Tensor neighbors_row_splits, bool align_corners=False, "
+            "str coordinate_mapping=\"ball_to_cube_radial\", bool normalize=False, "
+            "str interpolation=\"linear\", int max_temp_mem_MB=64) -> Tensor")
 
 _PLANS = {}
 
@@ -44,7 +51,14 @@ def _cuda_reduce(values, row_splits):
     return _k.reduce_subarrays_sum(values, row_splits)
 
 
-def _cuda_sparse_conv(filters, x, inp_importance, idx, kidx, nimp, rs, normalize):
+def _on(t, like):
+    """The reference passes CPU-constructed empty tensors for unused inputs (common_torch.py:130-136)."""
+    return t.to(like.device) if t.device != like.device and t.numel() == 0 else t
+
+
+def _cuda_sparse_conv(filters, x, inp_importance, idx, kidx, nimp, rs, normalize=False, max_temp_mem_MB=64):
+    # max_temp_mem_MB bounds Open3D's temporary B-matrix; this implementation has no such buffer
+    inp_importance, nimp = _on(inp_importance, x), _on(nimp, x)
     plan = _plan(idx, kidx, rs, filters.shape[0])
     has_imp = nimp.numel() > 0 or inp_importance.numel() > 0
     norm = None
@@ -59,7 +73,12 @@ def _cuda_sparse_conv(filters, x, inp_importance, idx, kidx, nimp, rs, normalize
 
 
 def _cuda_cconv(filters, out_positions, extents, offset, inp_positions, inp_features, inp_importance, idx, nimp, rs,
-                normalize):
+                align_corners=False, coordinate_mapping="ball_to_cube_radial", normalize=False, interpolation="linear",
+                max_temp_mem_MB=64):
+    if not (align_corners and coordinate_mapping == "ball_to_cube_radial" and interpolation == "linear"):
+        raise NotImplementedError("asr_b200 implements the configuration the reference uses: align_corners=True, "
+                                  "coordinate_mapping='ball_to_cube_radial', interpolation='linear'")
+    inp_importance, nimp = _on(inp_importance, inp_features), _on(nimp, inp_features)
     return _k.continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_features,
                               inp_importance if inp_importance.numel() else None, idx,
                               nimp if nimp.numel() else None, rs, normalize=normalize)
@@ -96,25 +115,18 @@ def reduce_subarrays_sum(values, row_splits):
     return torch.ops.open3d.reduce_subarrays_sum(values, row_splits)
 
 
-def _dev(t, like):
-    return t.to(like.device) if t.device != like.device and t.numel() == 0 else t
-
-
 def sparse_conv(filters, inp_features, inp_importance, neighbors_index, neighbors_kernel_index,
                 neighbors_importance, neighbors_row_splits, normalize=False, max_temp_mem_MB=64):
-    # the reference passes CPU-constructed empty tensors for the unused inputs (common_torch.py:130-136)
-    return torch.ops.open3d.sparse_conv(filters, inp_features, _dev(inp_importance, inp_features), neighbors_index,
-                                        neighbors_kernel_index, _dev(neighbors_importance, inp_features),
-                                        neighbors_row_splits, normalize)
+    return torch.ops.open3d.sparse_conv(filters, inp_features, inp_importance, neighbors_index,
+                                        neighbors_kernel_index, neighbors_importance, neighbors_row_splits,
+                                        normalize, max_temp_mem_MB)
 
 
 def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_features, inp_importance,
                     neighbors_index, neighbors_importance, neighbors_row_splits, align_corners=False,
                     coordinate_mapping="ball_to_cube_radial", normalize=False, interpolation="linear",
                     max_temp_mem_MB=64):
-    if not (align_corners and coordinate_mapping == "ball_to_cube_radial" and interpolation == "linear"):
-        raise NotImplementedError("asr_b200 implements the configuration the reference uses: align_corners=True, "
-                                  "coordinate_mapping='ball_to_cube_radial', interpolation='linear'")
     return torch.ops.open3d.continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_features,
-                                            _dev(inp_importance, inp_features), neighbors_index,
-                                            _dev(neighbors_importance, inp_features), neighbors_row_splits, normalize)
+                                            inp_importance, neighbors_index, neighbors_importance,
+                                            neighbors_row_splits, align_corners, coordinate_mapping, normalize,
+                                            interpolation, max_temp_mem_MB)

@@ -54,8 +54,8 @@ def conv_traffic_per_launch():
 
 
 def workload_name(args):
-    return "%s %.3gM pts, %d grid levels, full v0 U-Net (seeded random weights), fp32" % (
-        args.workload, args.points / 1e6, args.levels)
+    return "%s %.3gM pts (%s radii), %d grid levels, full v0 U-Net (seeded random weights), fp32" % (
+        args.workload, args.points / 1e6, "k=24 kNN" if args.radii == "knn" else "analytic", args.levels)
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -133,15 +133,36 @@ def algorithmic_bytes(sizes, convs):
     return b
 
 
+# ------------------------------------------------------------------------------------ workload
+def make_cloud(args, n_points, on_gpu):
+    """The synthetic cloud of the workload.  --radii knn (default): the per-point
+    radius is the distance to the 24th nearest neighbour (itself included, nsearch.cpp:38-48) — computed
+    OUTSIDE every timed region (the metric excludes the kNN pre-filter, §8d), by the GPU kNN kernel in the
+    GPU arm and by the float32 oracle (scipy cKDTree candidates) in the CPU legs; the two are bit-identical
+    (tests/test_gpu_configs.py).  --radii analytic keeps the generator's closed-form estimate (round 1)."""
+    from asr_b200 import clouds
+    cloud = clouds.make(args.workload, n_points, seed=args.seed)
+    if args.radii == "knn":
+        if on_gpu:
+            import torch
+            from asr_b200 import ops
+            tree = ops.KDTree(torch.from_numpy(cloud["points"]).cuda())
+            cloud["radii"] = tree.compute_k_radius(24).cpu().numpy()
+            del tree
+        else:
+            from oracle import ops_cpu
+            cloud["radii"] = ops_cpu.k_radius(cloud["points"], 24)
+    return cloud
+
+
 # ------------------------------------------------------------------------------------ CPU legs
 def cpu_pipeline_points_per_s(args, n_points, steps=1, warmup=0):
     """The oracle CPU path on `n_points` of the same workload, all host threads."""
     import torch
-    from asr_b200 import clouds
     from oracle import model_cpu, pipeline_cpu
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cloud = clouds.make(args.workload, n_points, seed=args.seed)
+    cloud = make_cloud(args, n_points, on_gpu=False)
     P = model_cpu.init_params(args.levels, seed=0, stress=True)
     times = {}
     for _ in range(warmup):
@@ -153,29 +174,86 @@ def cpu_pipeline_points_per_s(args, n_points, steps=1, warmup=0):
     dt = (time.perf_counter() - t0) / steps
     geom = times.get("geometry", "port")
     stage = {k: round(v, 4) for k, v in times.items() if k != "geometry"}
-    sample = ("%s cloud of %d points (same generator/seed), %d levels; geometry stages = %s (1 thread), search = scipy "
+    sample = ("%s cloud of %d points (same generator/seed, %s radii), %d levels; geometry stages = %s (1 thread), search = scipy "
               "cKDTree (all cores), network = torch-CPU restatement of the Open3D ops (%d threads); stage seconds %s"
-              % (args.workload, n_points, args.levels,
+              % (args.workload, n_points, args.radii, args.levels,
                  "reference cpp/lib TUs (oracle/_ref)" if geom == "reference" else "oracle port", cores,
                  json.dumps(stage)))
-    return n_points / dt, dt, cores, sample, int(out["values"].shape[0])
+    kind = "reference_tus+restatement" if geom == "reference" else "port"
+    return n_points / dt, dt, cores, sample, int(out["values"].shape[0]), kind
 
 
 def run_reference(args):
+    """`--impl reference`: the CPU path on the SAME cloud as the GPU arm (10 M points by default).  One pass
+    takes minutes, so the arm runs ONE timed step whatever --steps says (the line reports the steps it ran),
+    after --warmup passes over a 100 k-point cloud of the same generator (they warm the thread pools and the
+    allocator; a full-size warm-up pass would double the run).  --cpu-points N (< --points) bounds the sample
+    instead and says so in `config`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    v, dt, cores, sample, v0 = cpu_pipeline_points_per_s(args, args.cpu_points, steps=args.steps, warmup=min(args.warmup, 1))
+    n = args.points if args.cpu_points is None else min(args.cpu_points, args.points)
+    bounded = n < args.points
+    if args.warmup > 0:
+        cpu_pipeline_points_per_s(args, min(100_000, n), steps=min(args.warmup, 2))
+    steps = args.steps if bounded else 1
+    v, dt, cores, sample, v0, kind = cpu_pipeline_points_per_s(args, n, steps=steps)
+    cfg = {"workload": workload_name(args)}
+    if bounded:
+        cfg["bounded_sample_points"] = n
+    else:
+        cfg["reference_arm_steps"] = ("1 timed step on the full cloud (a CPU pass takes minutes; --steps %d was capped), "
+                                      "warm-up passes on a 100 k-point cloud" % args.steps)
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "bounded_sample_points": args.cpu_points},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ --verify
+def verify_geometry(args, cloud, out):
+    """Integer half of the bench cloud against the CPU oracle, array by array: leaves, the
+    nine grid arrays of every level, dual cells — bit-exact or the run aborts.  Geometry oracle = the reference's
+    own cpp/lib TUs (oracle/_ref) where that library exists, else the port.  The oracle is the checker here, never
+    the thing measured.  Writes gpurun_out/r2_parity_<points>.json."""
+    import numpy as np
+    from oracle import pipeline_cpu
+    t0 = time.perf_counter()
+    kind, Cls = pipeline_cpu.geometry_backend(True)
+    tree = Cls(cloud["points"], cloud["radii"], cloud["bb_min"], cloud["bb_max"], 1.0, 0, 21)
+    res = {"points": int(cloud["points"].shape[0]), "levels": args.levels, "workload": workload_name(args),
+           "geometry_oracle": kind, "arrays": {}}
+    ok = True
+
+    def cmp(name, a, b):
+        nonlocal ok
+        same = a.shape == b.shape and bool(np.array_equal(a, b))
+        res["arrays"][name] = {"equal": same, "shape": list(b.shape)}
+        ok = ok and same
+
+    cmp("leaves", out["octree"].leaves().cpu().numpy().view(np.uint64), tree.leaves())
+    cmp("dual_vertex_indices", out["dual_vertex_indices"].cpu().numpy().astype(np.uint64), tree.dual_vertex_indices())
+    d = out["input_dict"]
+    for i, g in enumerate(tree.grids(args.levels, True)):
+        for k, v in g.items():
+            if k != "voxel_keys":
+                cmp("%s%d" % (k, i), d[k + str(i)].cpu().numpy(), v)
+    res["all_equal"] = ok
+    res["oracle_seconds"] = round(time.perf_counter() - t0, 1)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    path = os.path.join(ROOT, "gpurun_out", "r2_parity_%dm.json" % round(args.points / 1e6))
+    with open(path, "w") as f:
+        json.dump(res, f, indent=1)
+    print("verify: %d arrays compared with the %s geometry oracle in %.0f s: %s -> %s" %
+          (len(res["arrays"]), kind, res["oracle_seconds"], "ALL EQUAL" if ok else "MISMATCH", path), file=sys.stderr)
+    if not ok:
+        raise SystemExit("bench.py --verify: geometry arrays differ from the oracle: %s" %
+                         [k for k, v in res["arrays"].items() if not v["equal"]])
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -200,7 +278,7 @@ def run_gpu(args):
 
     # N > 1: ONE cloud, the path sharded by output-voxel ranges across the ranks with a halo-row
     # exchange before every sharded convolution (asr_b200/shard.py) -> strong scaling
-    cloud = clouds.make(args.workload, args.points, seed=args.seed)
+    cloud = make_cloud(args, args.points, on_gpu=True)
     net = model.seeded_weights(model.UNet(args.levels), seed=0).cuda()
     if world > 1:
         # rows owned by contiguous index range (default) or by spatial region (ASR_SHARD=spatial: 19x
@@ -234,6 +312,8 @@ def run_gpu(args):
              "E": [int(d["neighbors_index%d" % i].shape[0]) for i in range(args.levels)],
              "P": int(d["aggregation_neighbors_index"].shape[0]), "D": int(out["dual_vertex_indices"].shape[0]),
              "M": int(out["vertices"].shape[0])}
+    if args.verify and rank == 0:
+        verify_geometry(args, cloud, out)
     del out, d
     for _ in range(max(args.warmup - 2, 0)):
         step_device()
@@ -348,8 +428,8 @@ def run_gpu(args):
             "stage_ms_synchronised_untimed_step": stage_ms, "kernel_ms": kernels,
         }
         if world == 1 and not args.no_cpu_baseline:
-            v, dt, cores, sample, _ = cpu_pipeline_points_per_s(args, args.cpu_points)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            v, dt, cores, sample, _, kind = cpu_pipeline_points_per_s(args, args.cpu_points or 200_000)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -365,7 +445,13 @@ def main():
     ap.add_argument("--points", type=int, default=10_000_000)
     ap.add_argument("--levels", type=int, default=6)
     ap.add_argument("--seed", type=int, default=2)
-    ap.add_argument("--cpu-points", type=int, default=200_000, help="bounded sample for the CPU legs")
+    ap.add_argument("--cpu-points", type=int, default=None,
+                    help="bounded sample for the CPU legs (default: 200 k for cpu_baseline, the full cloud for --impl reference)")
+    ap.add_argument("--radii", default="knn", choices=["knn", "analytic"],
+                    help="per-point radii: k=24 nearest-neighbour distance (SURVEY config 3) or the generator's closed form")
+    ap.add_argument("--verify", action="store_true",
+                    help="also compare the geometry arrays of the bench cloud with the CPU oracle (minutes; writes "
+                         "gpurun_out/r2_parity_<points>.json)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--backend", default="tensor", choices=["tensor", "fp32"], help="sparse-conv contraction")
     ap.add_argument("--conv-os", type=int, default=0, help="1: output-stationary kernel for the plain K=55 convs")

@@ -140,8 +140,9 @@ def aggregate(P, inp, dtype=None):
     return y, imp
 
 
-def unet(P, feats_and_importance, inp, levels=5, dtype=None):
-    """UNet5.unet (net_definitions_torch.py:535-638) for `levels` grids."""
+def unet(P, feats_and_importance, inp, levels=5, dtype=None, taps=None):
+    """UNet5.unet (net_definitions_torch.py:535-638) for `levels` grids.  taps: optional dict that
+    receives the per-level encoder outputs ("enc<l>") and decoder block outputs ("dec<l>")."""
     nb = [(inp["neighbors_index%d" % i], inp["neighbors_kernel_index%d" % i], inp["neighbors_row_splits%d" % i])
           for i in range(levels)]
     up = [(inp["up_neighbors_index%d" % i], inp["up_neighbors_kernel_index%d" % i],
@@ -159,10 +160,14 @@ def unet(P, feats_and_importance, inp, levels=5, dtype=None):
         x, imp = conv_block(P, down_name(l), x, down[l - 1], imp, split=True, dtype=dtype)
         x, imp = conv_block(P, "sparseconv_encblock%d" % l, x, nb[l], imp, split=True, dtype=dtype)
         skips.append(x)
+    if taps is not None:
+        taps.update({"enc%d" % l: s for l, s in enumerate(skips)})
     for l in range(levels - 2, -1, -1):
         x, _ = conv_block(P, "sparseconv_up%d" % l, x, up[l], dtype=dtype)
         x = torch.cat([x, skips[l]], -1) if l >= 1 else x + skips[0]
         x, _ = conv_block(P, "sparseconv_decblock%d" % l, x, nb[l], dtype=dtype)
+        if taps is not None:
+            taps["dec%d" % l] = x
     return x
 
 
