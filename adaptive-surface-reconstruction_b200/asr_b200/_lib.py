@@ -51,6 +51,17 @@ SIGNATURES = {
     "asr_packed_conv_filters_size": (_i64, [_i32, _i32, _i32]),
     "asr_pack_conv_filters": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "asr_sparse_conv": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "asr_gx_plan_begin": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _pp]),
+    "asr_gx_plan_finish": (_i32, [_vp, _vp, _pi64]),
+    "asr_gx_plan_destroy": (None, [_vp]),
+    "asr_gx_packed_filters_bytes": (_i64, [_i32, _i32, _i32]),
+    "asr_gx_pack_filters": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "asr_gx_from_f32": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "asr_gx_to_f32": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "asr_gx_scale_rows": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "asr_gx_conv": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32,
+                           _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp]),
+    "asr_gx_overflow": (_i32, [_vp, C.POINTER(C.c_int)]),
     "asr_reduce_subarrays_sum": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "asr_invert_neighbors_list": (_i32, [_i64, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _vp]),
     "asr_decode": (_i32, [_vp, _vp, _i64] + [_vp] * 9),

@@ -58,13 +58,14 @@ class _Block(torch.nn.Module):
             setattr(self, "conv%d" % j, SpecialSparseConv(cout, cout, kernel_size))
         self._fused = None
         self._packed = {}
+        self._gx = None
 
     def filters(self, j, K=ops):
         """Filter bank of conv j (1 = first conv, fused for the split form) in the
         form the active backend wants: packed hi/lo tiles for the tensor-core
         kernel (built once and cached), the fp32 tensor otherwise."""
         W = self.first_conv()[0] if j == 1 else getattr(self, "conv%d" % j).kernel
-        if getattr(K, "PackedFilters", None) is None or K.SPARSE_CONV_BACKEND != "tensor" or W.shape[2] > 256:
+        if getattr(K, "PackedFilters", None) is None or K.SPARSE_CONV_BACKEND not in ("tensor", "gx") or W.shape[2] > 256:
             return W
         p = self._packed.get(j)
         if p is None:
@@ -156,6 +157,7 @@ class UNet(torch.nn.Module):
             if isinstance(m, _Block):
                 m._fused = None
                 m._packed = {}
+                m._gx = None
         return r
 
     # ------------------------------------------------------------------ reference methods
@@ -195,6 +197,9 @@ class UNet(torch.nn.Module):
         """UNet5.unet (:535-638).  taps: optional dict that receives the encoder output of every
         level ("enc<l>", the skip tensors) and every decoder block's output ("dec<l>") for parity tests."""
         L, K = self.octree_levels, self.K
+        if K is ops and ops.SPARSE_CONV_BACKEND == "gx":
+            from . import gx  # split-half activations, TMA-gather tcgen05 kernel (csrc/spconv_gx.cu)
+            return gx.unet(self, feats1, input_dict, taps)
         P = self.plans(input_dict)
         x, imp = feats1
         skips = []
@@ -259,6 +264,7 @@ def seeded_weights(net, seed=0, scaled=True):
             if isinstance(m, _Block):
                 m._fused = None
                 m._packed = {}
+                m._gx = None
     return net
 
 

@@ -287,8 +287,13 @@ class ConvPlan:
             self._h = None
 
 
-# "tensor": tcgen05 3xTF32 contraction (default); "fp32": the FMA tile kernel
-SPARSE_CONV_BACKEND = "tensor"
+# Backend of the U-Net's sparse convolutions:
+#   "gx"     (default) split-half activations between layers, TMA row gather + fp16 hi/lo tcgen05 MMAs,
+#            output-stationary dense slots (csrc/spconv_gx.cu; model.UNet.unet only)
+#   "tensor" pair-major tcgen05 3xTF32 kernel on fp32 activations (round 1; also what the generic
+#            asr_sparse_conv / open3d::sparse_conv entry points run — the gx setting falls back to it there)
+#   "fp32"   the FMA tile kernel
+SPARSE_CONV_BACKEND = "gx"
 
 
 class PackedFilters:
@@ -310,6 +315,8 @@ def sparse_conv(plan, filters, inp_features, inp_importance=None, neighbors_impo
     """out[o] = sum_n imp_n * x[idx_n] @ filters[slot_n] (+ normalise, bias, ReLU).
     `filters` is a [K, Cin, Cout] tensor or a PackedFilters (pre-packed, tensor cores)."""
     backend = backend or SPARSE_CONV_BACKEND
+    if backend == "gx":
+        backend = "tensor"
     packed = None
     if isinstance(filters, PackedFilters):
         packed, filters = filters, None

@@ -6,6 +6,7 @@
 #include "profile.cuh"
 #include "search.h"
 #include "sparse_conv.h"
+#include "spconv_gx.h"
 
 namespace asrb {
 std::atomic<long long> g_kernel_launches{0};
@@ -52,6 +53,9 @@ struct asr_search {
 };
 struct asr_conv_plan {
     ConvPlan p;
+};
+struct asr_gx_plan {
+    gx::Plan p;
 };
 
 namespace {
@@ -103,6 +107,7 @@ int asr_set_option(const char* name, int value) {
         }
         else if (std::string(name) == "conv_row_block_shift") sparse_conv_row_block_shift(value);
         else if (std::string(name) == "tc_ntile") sparse_conv_tc_ntile(value);
+        else if (std::string(name) == "gx_acc_groups") gx::set_acc_groups(value);
         else if (std::string(name) == "tc_stages") sparse_conv_tc_tune(value, 0);
         else if (std::string(name) == "tc_row_groups") sparse_conv_tc_tune(0, value);
         else throw Error(kInvalidArgument, std::string("unknown option: ") + name);
@@ -323,6 +328,94 @@ int asr_sparse_conv(const asr_conv_plan* plan, const float* filters, const float
                             importance_col, normalize, normalize_col, normalizer, splits, bias, relu, out, S(stream));
     });
 }
+int asr_gx_plan_begin(const int32_t* idx, const uint8_t* slot, const int64_t* splits, int64_t num_out, int64_t num_in,
+                      int64_t num_entries, int kernel_size, int mode, void* stream, asr_gx_plan** out) {
+    return guarded([&] {
+        ASRB_REQUIRE(out, "null argument");
+        ASRB_REQUIRE(num_out >= 0 && num_in >= 0 && num_entries >= 0, "negative size");
+        auto h = std::make_unique<asr_gx_plan>();
+        gx::plan_begin(h->p, idx, slot, splits, num_out, num_in, num_entries, kernel_size, mode, S(stream));
+        *out = h.release();
+    });
+}
+int asr_gx_plan_finish(asr_gx_plan* plan, void* stream, int64_t* num_rare) {
+    return guarded([&] {
+        ASRB_REQUIRE(plan, "plan is null");
+        gx::plan_finish(plan->p, S(stream));
+        if (num_rare) *num_rare = plan->p.mode == gx::kModeStationary ? plan->p.R : 0;
+    });
+}
+void asr_gx_plan_destroy(asr_gx_plan* plan) { delete plan; }
+int64_t asr_gx_packed_filters_bytes(int kernel_size, int in_channels, int ncols) {
+    return (int64_t)gx::packed_filter_bytes(kernel_size, in_channels, ncols);
+}
+int asr_gx_pack_filters(const float* d_filters, int kernel_size, int in_channels, int out_channels, int col0, int ncols,
+                        int scale_exp, void* d_packed, void* stream) {
+    return guarded([&] {
+        ASRB_REQUIRE(d_filters && d_packed && kernel_size >= 1, "gx pack: null argument");
+        gx::pack_filters(d_filters, kernel_size, in_channels, out_channels, col0, ncols, scale_exp, d_packed, S(stream));
+    });
+}
+static gx::H2View h2view(const void* p, int64_t num_rows, int C, int pitch, int hi, int lo) {
+    gx::H2View v;
+    v.p = (__half*)p;
+    v.rows = num_rows + 1;
+    v.C = C;
+    v.pitch = pitch;
+    v.hi = hi;
+    v.lo = lo;
+    return v;
+}
+int asr_gx_from_f32(const float* d_x, int64_t num_rows, int channels, int ldx, const float* d_row_scale, void* d_out,
+                    int out_pitch, int out_hi, int out_lo, void* stream) {
+    return guarded([&] {
+        gx::from_f32(d_x, num_rows, channels, ldx, d_row_scale, h2view(d_out, num_rows, channels, out_pitch, out_hi, out_lo),
+                     S(stream));
+    });
+}
+int asr_gx_to_f32(const void* d_x, int64_t num_rows, int channels, int pitch, int hi, int lo, float* d_out, int ldo,
+                  void* stream) {
+    return guarded([&] { gx::to_f32(h2view(d_x, num_rows, channels, pitch, hi, lo), num_rows, d_out, ldo, S(stream)); });
+}
+int asr_gx_scale_rows(const void* d_x, int64_t num_rows, int channels, int pitch, int hi, int lo,
+                      const float* d_row_scale, void* d_out, int out_pitch, int out_hi, int out_lo, void* stream) {
+    return guarded([&] {
+        ASRB_REQUIRE(d_row_scale, "gx scale_rows: row_scale is null");
+        gx::scale_rows(h2view(d_x, num_rows, channels, pitch, hi, lo), num_rows, d_row_scale,
+                       h2view(d_out, num_rows, channels, out_pitch, out_hi, out_lo), S(stream));
+    });
+}
+int asr_gx_conv(const asr_gx_plan* plan, const void* d_x, int in_channels, int x_pitch, int x_hi, int x_lo,
+                const void* d_packed, int ncols, int scale_exp, const float* d_bias, int relu, const float* d_norm,
+                const float* d_imp, const void* d_res, int res_pitch, int res_hi, int res_lo, void* d_out_h2, int out_pitch, int out_hi,
+                int out_lo, float* d_out_f32, int out_f32_pitch, float* d_pairbuf, void* stream) {
+    return guarded([&] {
+        ASRB_REQUIRE(plan && d_x && d_packed, "gx conv: null argument");
+        gx::ConvArgs a;
+        a.x = h2view(d_x, plan->p.V_in, in_channels, x_pitch, x_hi, x_lo);
+        a.wp = d_packed;
+        a.K = plan->p.K;
+        a.ncols = ncols;
+        a.scale_exp = scale_exp;
+        a.bias = d_bias;
+        a.relu = relu;
+        a.norm = d_norm;
+        a.imp = d_imp;
+        if (d_res) a.res = h2view(d_res, plan->p.V, ncols, res_pitch, res_hi, res_lo);
+        if (d_out_h2) a.out = h2view(d_out_h2, plan->p.V, ncols, out_pitch, out_hi, out_lo);
+        a.out_f32 = d_out_f32;
+        a.out_f32_pitch = out_f32_pitch;
+        a.pairbuf = d_pairbuf;
+        gx::conv(plan->p, a, S(stream));
+    });
+}
+int asr_gx_overflow(void* stream, int* flag) {
+    return guarded([&] {
+        ASRB_REQUIRE(flag, "null argument");
+        *flag = gx::overflow_flag_read_and_clear(S(stream));
+    });
+}
+
 int asr_reduce_subarrays_sum(const float* values, const int32_t* index, const int64_t* splits, int64_t num_rows,
                              float* out, void* stream) {
     return guarded([&] { row_importance(values, index, splits, num_rows, out, S(stream)); });

@@ -9,9 +9,11 @@
 //
 //   points --point_group_kernel--> group key per point --sort/unique--> base groups
 //   base groups --ancestor_kernel--> <=20 ancestor groups each --sort/unique--> closure
-//   repeat: leaf first-siblings probe the 6 face neighbours of their parent
-//           (binary search in the sorted closure), missing chains are appended
-//           atomically, sorted, uniqued and merged   (round-synchronous 2:1 balance)
+//   repeat: leaf first-siblings probe the 6 face neighbours of their parent (hash probes of a
+//           snapshot), missing chains are appended atomically with their position in the reference's
+//           processing order, sorted, uniqued and merged; the rare keys whose leaf test the
+//           reference's SEQUENTIAL sweep would have decided differently (children created earlier in
+//           the same pass) are found and resolved afterwards  (2:1 balance, see octree_build)
 //   nodes = root + 8 x groups; leaf flag = first child group absent; scan -> leaves
 //
 // Results are bit-identical to the reference (tests/test_geometry_parity.py).
@@ -21,6 +23,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <vector>
 
 namespace asrb {
 
@@ -121,29 +124,70 @@ __device__ __forceinline__ bool has_group(const KeyTableView groups, Key g) { re
 // sibling is a leaf requires the 6 face neighbours of its parent to exist; for a
 // missing neighbour the chain of sibling groups up to the first existing
 // ancestor is appended to `out`.
+// rank of an insertion event in the reference's sequential sweep: (position of the processed key in
+// the pass, face, step of the chain walk) — the order in which octree.cpp:178-196 would create nodes
+constexpr unsigned long long kRankPerKey = 6ULL * 32ULL;
+
+__device__ __forceinline__ bool first_sibling_is_leaf(const KeyTableView groups, Key g) {
+    if (g == 0) return false;  // key 0 counts as having a first child (itself)
+    // leaf test on the first sibling (octreebase.h:174-182)
+    return !(__clzll((long long)g) > 1 && has_group(groups, g << 3));
+}
+
 __global__ void __launch_bounds__(256)
 balance_round_kernel(const Key* __restrict__ frontier, long long nf, const KeyTableView groups,
-                     Key* __restrict__ out, unsigned long long cap,
+                     Key* __restrict__ out, unsigned long long* __restrict__ out_rank, unsigned long long cap,
                      unsigned long long* __restrict__ out_count) {
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= nf * 6) return;
     const Key g = frontier[t / 6];
     const int face = (int)(t % 6);
-    if (g == 0) return;  // key 0 counts as having a first child (itself)
-    // leaf test on the first sibling (octreebase.h:174-182)
-    if (__clzll((long long)g) > 1 && has_group(groups, g << 3)) return;
+    if (!first_sibling_is_leaf(groups, g)) return;
     const Cell pc = key_cell(g >> 3);
     int d[3] = {0, 0, 0};
     d[face % 3] = face < 3 ? -1 : 1;
     Key k = cell_key(pc.x + d[0], pc.y + d[1], pc.z + d[2], pc.lev);
     if (!k) return;
+    unsigned long long step = 0;
     while (k > 1) {
         const Key kg = k & ~Key(7);
         if (has_group(groups, kg)) break;
         const unsigned long long pos = atomicAdd(out_count, 1ULL);
-        if (pos < cap) out[pos] = kg;
+        if (pos < cap) {
+            out[pos] = kg;
+            out_rank[pos] = (unsigned long long)t * 32ULL + step;
+        }
+        ++step;
         k >>= 3;
     }
+}
+
+// first record of every run of equal keys (records sorted by (key, rank)): the group and its earliest creation
+__global__ void __launch_bounds__(256)
+record_heads_kernel(const Key* __restrict__ key, const unsigned long long* __restrict__ rank, long long n,
+                    Key* __restrict__ out_key, unsigned long long* __restrict__ out_rank,
+                    unsigned long long* __restrict__ count) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (i > 0 && key[i - 1] == key[i]) return;
+    const unsigned long long pos = atomicAdd(count, 1ULL);
+    out_key[pos] = key[i];
+    out_rank[pos] = rank[i];
+}
+
+// keys of the pass that are leaves in the snapshot but whose children are created during this very pass: the
+// sequential sweep skips such a key if the creation comes first (octree.cpp:171) -> candidates for the host
+__global__ void __launch_bounds__(256)
+balance_candidates_kernel(const Key* __restrict__ frontier, long long nf, const KeyTableView groups,
+                          const Key* __restrict__ new_keys, long long nn, long long* __restrict__ cand_pos,
+                          unsigned long long cap, unsigned long long* __restrict__ count) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= nf) return;
+    const Key g = frontier[i];
+    if (__clzll((long long)g) <= 1 || !first_sibling_is_leaf(groups, g)) return;
+    if (find_key(new_keys, nn, g << 3) < 0) return;
+    const unsigned long long pos = atomicAdd(count, 1ULL);
+    if (pos < cap) cand_pos[pos] = i;
 }
 
 __global__ void __launch_bounds__(256)
@@ -221,23 +265,33 @@ void octree_build(Octree& t, const float* d_points, const float* d_radii, int64_
     if (ng) ASRB_CUDA(cudaMemcpyAsync(groups.get(), all.get(), ng * sizeof(Key), cudaMemcpyDeviceToDevice, s));
     all.release();
 
-    // 3. 2:1 face balance to a fixed point
+    // 3. 2:1 face balance to a fixed point (octree.cpp:152-206).
+    // The reference sweeps the first-sibling keys SEQUENTIALLY — pass 1 in the iteration order of its hash map
+    // (ascending keys for the pinned oracle, oracle/shim/libcuckoo), every later pass in the order in which the
+    // previous pass created groups — and tests "is this key a leaf?" against the nodes inserted so far.  A pass
+    // here evaluates all keys against a snapshot and records, for every missing group, the rank (key position,
+    // face, chain step) of each event that would create it; the earliest rank per group gives the creation order
+    // (= next pass's order).  A key whose children are created by an EARLIER event of the same pass would have been
+    // skipped by the sequential sweep: such keys are rare (17 at 10 M points, none below a few million), they are
+    // detected on the device and resolved on the host in sweep order; their events are then withdrawn.
     DevBuf<Key> frontier(ng, s);
     size_t nf = ng;
     if (ng) ASRB_CUDA(cudaMemcpyAsync(frontier.get(), groups.get(), ng * sizeof(Key), cudaMemcpyDeviceToDevice, s));
-    DevBuf<unsigned long long> counter(1, s);
+    DevBuf<unsigned long long> counter(2, s);
     t.balance_rounds = 0;
     KeyTable table;
     while (nf > 0) {
         table.build(groups.get(), ng, s);
         size_t cap = std::max<size_t>(nf * 4, 1 << 16);
-        DevBuf<Key> emitted;
+        DevBuf<Key> rec_key;
+        DevBuf<unsigned long long> rec_rank;
         unsigned long long produced = 0;
         for (;;) {
-            emitted.alloc(cap, s);
-            ASRB_CUDA(cudaMemsetAsync(counter.get(), 0, sizeof(unsigned long long), s));
+            rec_key.alloc(cap, s);
+            rec_rank.alloc(cap, s);
+            ASRB_CUDA(cudaMemsetAsync(counter.get(), 0, 2 * sizeof(unsigned long long), s));
             balance_round_kernel<<<grid_for(nf * 6, 256), 256, 0, s>>>(frontier.get(), (long long)nf, table.view(),
-                                                                      emitted.get(), cap, counter.get());
+                                                                      rec_key.get(), rec_rank.get(), cap, counter.get());
             ASRB_CHECK_LAUNCH();
             produced = d2h_scalar(counter.get(), s);
             if (produced <= cap) break;
@@ -245,17 +299,88 @@ void octree_build(Octree& t, const float* d_points, const float* d_radii, int64_
         }
         ++t.balance_rounds;
         if (produced == 0) break;
-        sort_keys_u64(emitted.get(), (size_t)produced, s);
-        size_t nn = unique_u64(emitted.get(), (size_t)produced, s);
+        // records ordered by (group, rank): stable radix sorts, rank first
+        sort_pairs_u64_u64((Key*)rec_rank.get(), (unsigned long long*)rec_key.get(), (size_t)produced, s);
+        sort_pairs_u64_u64(rec_key.get(), rec_rank.get(), (size_t)produced, s);
+        DevBuf<Key> new_key((size_t)produced, s);
+        DevBuf<unsigned long long> new_rank((size_t)produced, s);
+        ASRB_CUDA(cudaMemsetAsync(counter.get(), 0, 2 * sizeof(unsigned long long), s));
+        record_heads_kernel<<<grid_for(produced, 256), 256, 0, s>>>(rec_key.get(), rec_rank.get(), (long long)produced,
+                                                                   new_key.get(), new_rank.get(), counter.get());
+        ASRB_CHECK_LAUNCH();
+        size_t nn = (size_t)d2h_scalar(counter.get(), s);
+        sort_pairs_u64_u64(new_key.get(), new_rank.get(), nn, s);  // the heads were appended in arbitrary order
+        const size_t cand_cap = 1 << 16;
+        DevBuf<long long> cand(cand_cap, s);
+        balance_candidates_kernel<<<grid_for(nf, 256), 256, 0, s>>>(frontier.get(), (long long)nf, table.view(),
+                                                                   new_key.get(), (long long)nn, cand.get(), cand_cap,
+                                                                   counter.get() + 1);
+        ASRB_CHECK_LAUNCH();
+        const size_t nc = (size_t)d2h_scalar(counter.get() + 1, s);
+        if (nc > 0) {
+            // sequential resolution on the host, in sweep order
+            ASRB_REQUIRE(nc <= cand_cap, "octree balance: too many order-dependent keys in one pass");
+            std::vector<long long> cpos(nc);
+            std::vector<Key> hk((size_t)produced);
+            std::vector<unsigned long long> hr((size_t)produced);
+            ASRB_CUDA(cudaMemcpyAsync(cpos.data(), cand.get(), nc * sizeof(long long), cudaMemcpyDeviceToHost, s));
+            ASRB_CUDA(cudaMemcpyAsync(hk.data(), rec_key.get(), produced * sizeof(Key), cudaMemcpyDeviceToHost, s));
+            ASRB_CUDA(cudaMemcpyAsync(hr.data(), rec_rank.get(), produced * sizeof(unsigned long long),
+                                      cudaMemcpyDeviceToHost, s));
+            ASRB_CUDA(cudaStreamSynchronize(s));
+            std::sort(cpos.begin(), cpos.end());
+            std::vector<Key> ckey(nc);
+            for (size_t c = 0; c < nc; ++c)
+                ASRB_CUDA(cudaMemcpyAsync(&ckey[c], frontier.get() + cpos[c], sizeof(Key), cudaMemcpyDeviceToHost, s));
+            ASRB_CUDA(cudaStreamSynchronize(s));
+            std::vector<char> invalid(nc, 0);
+            auto emitter_invalid = [&](unsigned long long j) {
+                auto it = std::lower_bound(cpos.begin(), cpos.end(), (long long)j);
+                return it != cpos.end() && *it == (long long)j && invalid[it - cpos.begin()];
+            };
+            bool any_invalid = false;
+            for (size_t c = 0; c < nc; ++c) {
+                const Key child = ckey[c] << 3;
+                size_t p = std::lower_bound(hk.begin(), hk.end(), child) - hk.begin();
+                for (; p < hk.size() && hk[p] == child; ++p) {
+                    const unsigned long long j = hr[p] / kRankPerKey;
+                    if (j >= (unsigned long long)cpos[c]) break;  // records of a key are ordered by rank
+                    if (!emitter_invalid(j)) {
+                        invalid[c] = 1;
+                        any_invalid = true;
+                        break;
+                    }
+                }
+            }
+            if (any_invalid) {
+                // withdraw the events of the skipped keys and rebuild the list of created groups
+                std::vector<Key> nk;
+                std::vector<unsigned long long> nr;
+                for (size_t p = 0; p < hk.size(); ++p) {
+                    if (emitter_invalid(hr[p] / kRankPerKey)) continue;
+                    if (!nk.empty() && nk.back() == hk[p]) continue;  // (key, rank) order: the first survivor is the earliest
+                    nk.push_back(hk[p]);
+                    nr.push_back(hr[p]);
+                }
+                nn = nk.size();
+                ASRB_CUDA(cudaMemcpyAsync(new_key.get(), nk.data(), nn * sizeof(Key), cudaMemcpyHostToDevice, s));
+                ASRB_CUDA(cudaMemcpyAsync(new_rank.get(), nr.data(), nn * sizeof(unsigned long long),
+                                          cudaMemcpyHostToDevice, s));
+                ASRB_CUDA(cudaStreamSynchronize(s));
+            }
+        }
+        if (nn == 0) break;
         // merge: the new groups are disjoint from `groups` by construction
         DevBuf<Key> merged(ng + nn, s);
         ASRB_CUDA(cudaMemcpyAsync(merged.get(), groups.get(), ng * sizeof(Key), cudaMemcpyDeviceToDevice, s));
-        ASRB_CUDA(cudaMemcpyAsync(merged.get() + ng, emitted.get(), nn * sizeof(Key), cudaMemcpyDeviceToDevice, s));
+        ASRB_CUDA(cudaMemcpyAsync(merged.get() + ng, new_key.get(), nn * sizeof(Key), cudaMemcpyDeviceToDevice, s));
         sort_keys_u64(merged.get(), ng + nn, s);
         groups = std::move(merged);
         ng += nn;
+        // next pass: the created groups in creation order
+        sort_pairs_u64_u64((Key*)new_rank.get(), (unsigned long long*)new_key.get(), nn, s);
         frontier.alloc(nn, s);
-        ASRB_CUDA(cudaMemcpyAsync(frontier.get(), emitted.get(), nn * sizeof(Key), cudaMemcpyDeviceToDevice, s));
+        ASRB_CUDA(cudaMemcpyAsync(frontier.get(), new_key.get(), nn * sizeof(Key), cudaMemcpyDeviceToDevice, s));
         nf = nn;
     }
 

@@ -49,6 +49,7 @@ static void sort_pairs_impl(K* d_keys, V* d_vals, size_t n, cudaStream_t s, int 
 
 void sort_keys_u64(Key* d_keys, size_t n, cudaStream_t s, int end_bit) { sort_keys_impl(d_keys, n, s, end_bit); }
 void sort_pairs_u64_u32(Key* k, uint32_t* v, size_t n, cudaStream_t s, int end_bit) { sort_pairs_impl(k, v, n, s, end_bit); }
+void sort_pairs_u64_u64(Key* k, unsigned long long* v, size_t n, cudaStream_t s, int end_bit) { sort_pairs_impl(k, v, n, s, end_bit); }
 void sort_pairs_u32_u32(uint32_t* k, uint32_t* v, size_t n, cudaStream_t s, int end_bit) { sort_pairs_impl(k, v, n, s, end_bit); }
 void sort_pairs_u8_u32(uint8_t* k, uint32_t* v, size_t n, cudaStream_t s, int end_bit) { sort_pairs_impl(k, v, n, s, end_bit); }
 

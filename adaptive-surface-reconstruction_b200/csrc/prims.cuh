@@ -10,6 +10,7 @@ namespace asrb {
 void sort_keys_u64(Key* d_keys, size_t n, cudaStream_t s, int end_bit = 64);
 // ascending stable sort of (key, value) pairs, in place
 void sort_pairs_u64_u32(Key* d_keys, uint32_t* d_vals, size_t n, cudaStream_t s, int end_bit = 64);
+void sort_pairs_u64_u64(Key* d_keys, unsigned long long* d_vals, size_t n, cudaStream_t s, int end_bit = 64);
 void sort_pairs_u32_u32(uint32_t* d_keys, uint32_t* d_vals, size_t n, cudaStream_t s, int end_bit = 32);
 void sort_pairs_u8_u32(uint8_t* d_keys, uint32_t* d_vals, size_t n, cudaStream_t s, int end_bit = 8);
 // removes consecutive duplicates of a sorted array in place; returns new length (synchronises)

@@ -672,7 +672,7 @@ void knn_build(Search& S, const float* d_points, int64_t n, cudaStream_t s) {
 }
 
 void knn_radius(const Search& S, int k, float* d_out, cudaStream_t s) {
-    ASRB_REQUIRE(k >= 1 && k <= 32, "k must be in [1, 32]");
+    ASRB_REQUIRE(k >= 1 && k <= 32, "asr_b200 kNN: k must be in [1, 32] (the reference default is 24; the warp-wide candidate list holds 32 entries)");
     if (S.n == 0) return;
     ProfileScope prof("knn_radius", s);
     knn_kernel<false><<<grid_for(S.n, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
@@ -682,7 +682,7 @@ void knn_radius(const Search& S, int k, float* d_out, cudaStream_t s) {
 
 void knn_inlier(const Search& S, const float* d_radii, float fraction, int k, int outlier_threshold, uint8_t* d_out,
                 cudaStream_t s) {
-    ASRB_REQUIRE(k >= 1 && k <= 32, "k must be in [1, 32]");
+    ASRB_REQUIRE(k >= 1 && k <= 32, "asr_b200 kNN: k must be in [1, 32] (the reference default is 24; the warp-wide candidate list holds 32 entries)");
     if (S.n == 0) return;
     ProfileScope prof("knn_inlier", s);
     knn_kernel<true><<<grid_for(S.n, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(

@@ -35,6 +35,9 @@
 #include "profile.cuh"
 #include "sparse_conv.h"
 
+#include <mutex>
+#include <vector>
+
 namespace asrb {
 
 constexpr int TM = 128;        // pairs per tile
@@ -164,6 +167,29 @@ tile_list_kernel(int K, int num_blocks, int tile_rows, const long long* __restri
     }
 }
 
+// Pinned host ints for the plans' "exactly one slot-0 entry per row" flags: slots are handed out from
+// pooled pinned pages under a mutex and returned by ~ConvPlan, so a pending plan's slot is never reused.
+namespace {
+std::mutex g_flag_mutex;
+std::vector<int*> g_flag_free;
+}  // namespace
+int* flag_slot_acquire() {
+    std::lock_guard<std::mutex> lock(g_flag_mutex);
+    if (g_flag_free.empty()) {
+        int* page = nullptr;
+        ASRB_CUDA(cudaMallocHost((void**)&page, 256 * sizeof(int)));  // never freed: lives as long as the library
+        for (int i = 0; i < 256; ++i) g_flag_free.push_back(page + i);
+    }
+    int* p = g_flag_free.back();
+    g_flag_free.pop_back();
+    return p;
+}
+void flag_slot_release(int* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_flag_mutex);
+    g_flag_free.push_back(p);
+}
+
 void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, const int64_t* d_splits, int64_t V_out,
                      int64_t E, int K, cudaStream_t s, bool with_output_stationary) {
     ASRB_REQUIRE(K >= 1 && K <= 256, "sparse_conv: kernel_size must be in [1, 256]");
@@ -228,10 +254,7 @@ void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, c
             const int64_t r = std::min<int64_t>(rows_per_block, V_out - b * rows_per_block);
             P.tiles0_if_flag += (int)((r + TM - 1) / TM);
         }
-        static int* pool = nullptr;
-        static unsigned next = 0;
-        if (!pool) ASRB_CUDA(cudaMallocHost((void**)&pool, 1024 * sizeof(int)));
-        P.flag_host = pool + (next++ % 1024);
+        if (!P.flag_host) P.flag_host = flag_slot_acquire();  // owned by the plan until its destructor
         *P.flag_host = 1;
         if (!P.flag_event) ASRB_CUDA(cudaEventCreateWithFlags(&P.flag_event, cudaEventDisableTiming));
         ASRB_CUDA(cudaMemcpyAsync(P.flag_host, flag.get(), sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -27,9 +27,7 @@ struct ConvPlan {
     mutable bool flag_pending = false;  // the device flag is still on its way to *flag_host
     int* flag_host = nullptr;
     cudaEvent_t flag_event = nullptr;
-    ~ConvPlan() {
-        if (flag_event) cudaEventDestroy(flag_event);
-    }
+    ~ConvPlan();
     DevBuf<long long> g_begin;
     DevBuf<int> g_tile0;
     bool has_tiles2 = false;      // built only when the 2-row-group option is on at plan creation
@@ -45,6 +43,16 @@ struct ConvPlan {
     DevBuf<int32_t> os_idx;   // [os_steps][256]
     std::unique_ptr<ConvPlan> rare;  // entries of the slots that are not accumulated output-stationary
 };
+
+int* flag_slot_acquire();
+void flag_slot_release(int* p);
+inline ConvPlan::~ConvPlan() {
+    if (flag_event) {
+        if (flag_pending) cudaEventSynchronize(flag_event);  // the async copy into the slot must have landed
+        cudaEventDestroy(flag_event);
+    }
+    flag_slot_release(flag_host);
+}
 
 void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, const int64_t* d_splits, int64_t V_out,
                      int64_t E, int K, cudaStream_t s, bool with_output_stationary = true);

@@ -1,0 +1,945 @@
+// "gx" generalized sparse convolution for the U-Net (reference models/common_torch.py:95-148,
+// models/v0/net_definitions_torch.py:123-387 -> Open3D `sparse_conv`):
+//
+//     out[o, :] = act( sum_{n in row(o)} x[idx_n, :] @ W[slot_n] (/ norm[o]) + bias ) (+ residual[o, :])
+//
+// B200 design (round 2; replaces the pair-major scatter kernels of round 1 on the model's path):
+//
+//  * Activations live in HBM in a split-half format between layers: x = hi + lo with two fp16 planes per
+//    row (same 4 bytes per element as fp32; |x| < 65504, 22+ significant bits for |x| >= 2^-3, absolute
+//    error <= 2^-25 below).  Gathered rows are then tensor-core operands AS THEY LIE in memory: the TMA
+//    engine gathers them (cp.async.bulk.tensor ... tile::gather4, 4 rows x 128 bytes per instruction,
+//    128-byte swizzle) straight into the K-major operand tile — no LSU traffic, no register staging, no
+//    conversion pass, no generic->async proxy fence.
+//  * fp32-accurate product on the fp16 pipe (2x the tf32 rate, half the operand bytes of 3xTF32):
+//    D += A_hi B_hi + A_lo B_hi + A_hi B_lo; hi*hi products are exact in fp32, the dropped lo*lo term is
+//    2^-22 relative.  Filters are packed once per bank as fp16 hi / lo of W * 2^e in the kernel's shared-
+//    memory image (one bulk copy per slot and 64-channel chunk).
+//  * Output-stationary for the DENSE kernel slots (self + the 6 same-level faces, 73 % of the entries;
+//    the 8 child slots of the down tables): one CTA tile = 128 consecutive output rows, accumulators in
+//    TMEM across all dense slots, each output row written ONCE with bias / ReLU / normalisation /
+//    residual / re-splitting fused — no atomics, no zero fill, no separate epilogue pass, bit-
+//    reproducible.  Absent neighbours gather an all-zero row.
+//  * The RARE slots (finer / coarser neighbours at level transitions: 27 % of the entries spread over 48
+//    slots, present in 87 % of the rows but never dense in any row tile, measured on the bench cloud) run
+//    pair-major: entries sorted by (32768-row block, slot) fill 128-pair tiles; their products go to a
+//    compact pair buffer in ROW order, which the output-stationary epilogue of the owning row reads back
+//    as one contiguous segment (plain stores and loads, no reductions in L2).
+//  * One persistent warp-specialised kernel (TMA warp / MMA thread / 4 epilogue warps), TMEM double
+//    buffered so the epilogue of tile i overlaps the MMAs of tile i + 1.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "internal.h"
+#include "prims.cuh"
+#include "profile.cuh"
+#include "spconv_gx.h"
+#include "umma.cuh"
+
+namespace asrb {
+namespace gx {
+
+static int g_acc_groups = 0;  // dev knob: main-accumulator groups per TMEM buffer (0 = as many as fit, <= 4)
+void set_acc_groups(int g) { g_acc_groups = g; }
+
+namespace {
+constexpr int kRowBlockShift = 15;  // rare entries are grouped by blocks of 2^15 output rows
+constexpr int kThreads = 192;       // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr uint32_t kATile = kTM * 128;  // 128 rows x 128 bytes
+
+__device__ int g_overflow_flag = 0;
+
+// ------------------------------------------------------------------------------------------ plan
+// rare entries (slot >= D) per row
+__global__ void __launch_bounds__(256)
+rare_count_kernel(const int64_t* __restrict__ splits, const uint8_t* __restrict__ slot, long long V, int D,
+                  int32_t* __restrict__ cnt) {
+    const long long v = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3;
+    const int sub = threadIdx.x & 7;
+    int n = 0;
+    if (v < V) {
+        const int64_t e = splits[v + 1];
+        for (int64_t j = splits[v] + sub; j < e; j += 8) n += slot[j] >= D;
+    }
+    n += __shfl_xor_sync(0xffffffffu, n, 1);
+    n += __shfl_xor_sync(0xffffffffu, n, 2);
+    n += __shfl_xor_sync(0xffffffffu, n, 4);
+    if (v < V && sub == 0) cnt[v] = n;
+}
+
+__global__ void __launch_bounds__(256) fill_i32_kernel(int32_t* __restrict__ p, long long n, int32_t v) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// dense entries -> gather table; rare entries -> (sort key, source row) at their row-major rare position
+__global__ void __launch_bounds__(256)
+plan_fill_kernel(const int64_t* __restrict__ splits, const int32_t* __restrict__ idx, const uint8_t* __restrict__ slot,
+                 long long V, int D, const int64_t* __restrict__ rare_rs, int32_t* __restrict__ gidx,
+                 uint32_t* __restrict__ rare_key, int32_t* __restrict__ rare_src) {
+    const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    int64_t p = rare_rs[v];
+    const int64_t e = splits[v + 1];
+    for (int64_t j = splits[v]; j < e; ++j) {
+        const int k = slot[j];
+        if (k < D) {
+            gidx[((v >> 7) * D + k) * kTM + (v & 127)] = idx[j];
+        } else {
+            rare_key[p] = ((uint32_t)(v >> kRowBlockShift) << 8) | (uint32_t)k;
+            rare_src[p] = idx[j];
+            ++p;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) iota_u32_kernel(uint32_t* __restrict__ p, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (uint32_t)i;
+}
+
+__device__ __forceinline__ long long lower_bound_u32(const uint32_t* a, long long n, uint32_t k) {
+    long long lo = 0, hi = n;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (a[mid] < k) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// first sorted rare entry of every (row block, slot) group; g = block * K + slot
+__global__ void __launch_bounds__(256)
+group_begin_kernel(const uint32_t* __restrict__ sorted_key, long long R, int K, int G, long long* __restrict__ g_begin) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > G) return;
+    if (g == G) {
+        g_begin[g] = R;
+        return;
+    }
+    const uint32_t key = ((uint32_t)(g / K) << 8) | (uint32_t)(g % K);
+    g_begin[g] = lower_bound_u32(sorted_key, R, key);
+}
+
+// one block: 128-pair tiles of the groups (slot, first entry, count)
+__global__ void __launch_bounds__(256)
+pair_tile_list_kernel(int K, int G, const long long* __restrict__ g_begin, int4* __restrict__ tiles,
+                      int* __restrict__ num_tiles) {
+    __shared__ int s_part[256];
+    const int chunk = (G + 255) / 256;
+    const int g0 = min(G, (int)threadIdx.x * chunk), g1 = min(G, g0 + chunk);
+    int sum = 0;
+    for (int g = g0; g < g1; ++g) sum += (int)((g_begin[g + 1] - g_begin[g] + kTM - 1) / kTM);
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < 256; ++i) {
+            const int v = s_part[i];
+            s_part[i] = t;
+            t += v;
+        }
+        *num_tiles = t;
+    }
+    __syncthreads();
+    int t = s_part[threadIdx.x];
+    for (int g = g0; g < g1; ++g) {
+        const long long b = g_begin[g], e = g_begin[g + 1];
+        for (long long start = b; start < e; start += kTM)
+            tiles[t++] = make_int4(g % K, (int)start, (int)min((long long)kTM, e - start), 0);
+    }
+}
+
+// per pair tile: gather rows and destinations of its 128 lanes
+__global__ void __launch_bounds__(kTM)
+pair_tile_fill_kernel(const int4* __restrict__ tiles, const int* __restrict__ num_tiles, const uint32_t* __restrict__ perm,
+                      const int32_t* __restrict__ rare_src, const int32_t* __restrict__ out_row, int32_t zero_row,
+                      int32_t* __restrict__ pt_slot, int32_t* __restrict__ pt_gidx, int32_t* __restrict__ pt_out) {
+    const int t = blockIdx.x;
+    if (t >= *num_tiles) return;
+    const int4 tile = tiles[t];
+    const int r = threadIdx.x;
+    int src = zero_row, dst = -1;
+    if (r < tile.z) {
+        const uint32_t p = perm[tile.y + r];
+        src = rare_src[p];
+        dst = out_row ? out_row[p] : (int32_t)p;
+    }
+    pt_gidx[(size_t)t * kTM + r] = src;
+    pt_out[(size_t)t * kTM + r] = dst;
+    if (r == 0) pt_slot[t] = tile.x;
+}
+
+// row of every CSR entry (kModePairFinal: the destination of a pair is its output row)
+__global__ void __launch_bounds__(256)
+entry_row_kernel(const int64_t* __restrict__ splits, long long V, int32_t* __restrict__ rows) {
+    const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    for (int64_t j = splits[v]; j < splits[v + 1]; ++j) rows[j] = (int32_t)v;
+}
+
+}  // namespace
+
+Plan::~Plan() {
+    if (R_event) cudaEventDestroy(R_event);
+    if (R_host) cudaFreeHost(R_host);
+}
+
+void plan_begin(Plan& P, const int32_t* d_idx, const uint8_t* d_slot, const int64_t* d_splits, int64_t V, int64_t V_in,
+                int64_t E, int K, int mode, cudaStream_t s) {
+    ASRB_REQUIRE(K >= 1 && K <= 255, "gx plan: kernel_size must be in [1, 255]");
+    ASRB_REQUIRE(V < (int64_t(1) << 31) - 2 && V_in < (int64_t(1) << 31) - 2 && E < (int64_t(1) << 31),
+                 "gx plan: table too large");
+    P.V_in = V_in;
+    ASRB_REQUIRE(mode == kModeStationary || mode == kModePairFinal, "gx plan: bad mode");
+    P.mode = mode;
+    P.V = V;
+    P.E = E;
+    P.K = K;
+    // dense slots: the self slot and the six same-level faces of a within-grid table (grid.cpp:102-124), the
+    // eight child slots of a down table (inverted up table, grid.cpp:217-242); none for the pair-final form
+    P.D = mode == kModePairFinal ? 0 : (K == 55 ? 7 : std::min(K, 8));
+    P.T = (V + kTM - 1) / kTM;
+    P.d_idx = d_idx;
+    P.d_slot = d_slot;
+    P.d_splits = d_splits;
+    P.rare_rs.alloc((size_t)V + 1, s);
+    ProfileScope prof("gx_plan_build", s);
+    DevBuf<int32_t> cnt((size_t)std::max<int64_t>(V, 1), s);
+    if (V > 0) {
+        rare_count_kernel<<<grid_for((size_t)V * 8, 256), 256, 0, s>>>(d_splits, d_slot, V, P.D, cnt.get());
+        ASRB_CHECK_LAUNCH();
+    }
+    exclusive_sum_i32_to_i64(cnt.get(), P.rare_rs.get(), (size_t)V, s);
+    if (!P.R_host) ASRB_CUDA(cudaMallocHost((void**)&P.R_host, sizeof(int64_t)));
+    if (!P.R_event) ASRB_CUDA(cudaEventCreateWithFlags(&P.R_event, cudaEventDisableTiming));
+    ASRB_CUDA(cudaMemcpyAsync(P.R_host, P.rare_rs.get() + V, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    ASRB_CUDA(cudaEventRecord(P.R_event, s));
+    P.finished = false;
+}
+
+void plan_finish(Plan& P, cudaStream_t s) {
+    if (P.finished) return;
+    ASRB_CUDA(cudaEventSynchronize(P.R_event));
+    P.R = *P.R_host;
+    const int64_t V = P.V, R = P.R;
+    const int32_t zero_row = (int32_t)P.V_in;  // the all-zero row that follows the input tensor's rows
+    ProfileScope prof("gx_plan_build", s);
+    if (P.D > 0) {
+        const size_t n = (size_t)P.T * P.D * kTM;
+        P.gidx.alloc(std::max<size_t>(n, 1), s);
+        if (n) {
+            fill_i32_kernel<<<grid_for(n, 256), 256, 0, s>>>(P.gidx.get(), (long long)n, zero_row);
+            ASRB_CHECK_LAUNCH();
+        }
+    }
+    DevBuf<uint32_t> key((size_t)std::max<int64_t>(R, 1), s), perm((size_t)std::max<int64_t>(R, 1), s);
+    P.rare_in.alloc((size_t)std::max<int64_t>(R, 1), s);
+    DevBuf<int32_t>& src = P.rare_in;
+    if (V > 0) {
+        plan_fill_kernel<<<grid_for((size_t)V, 256), 256, 0, s>>>(P.d_splits, P.d_idx, P.d_slot, V, P.D, P.rare_rs.get(),
+                                                                 P.gidx.get(), key.get(), src.get());
+        ASRB_CHECK_LAUNCH();
+    }
+    const int num_blocks = (int)std::max<int64_t>((V + (int64_t(1) << kRowBlockShift) - 1) >> kRowBlockShift, 1);
+    const int G = num_blocks * P.K;
+    P.max_pair_tiles = (int)(R / kTM) + G + 1;
+    P.pt_slot.alloc((size_t)P.max_pair_tiles, s);
+    P.pt_gidx.alloc((size_t)P.max_pair_tiles * kTM, s);
+    P.pt_out.alloc((size_t)P.max_pair_tiles * kTM, s);
+    P.pt_count.alloc(1, s);
+    if (R > 0) {
+        iota_u32_kernel<<<grid_for((size_t)R, 256), 256, 0, s>>>(perm.get(), R);
+        ASRB_CHECK_LAUNCH();
+        int bits = 8;
+        while (bits < 31 && (int64_t(1) << (bits - 8)) < num_blocks) ++bits;
+        sort_pairs_u32_u32(key.get(), perm.get(), (size_t)R, s, bits);
+        DevBuf<long long> g_begin((size_t)G + 1, s);
+        group_begin_kernel<<<grid_for((size_t)G + 1, 256), 256, 0, s>>>(key.get(), R, P.K, G, g_begin.get());
+        ASRB_CHECK_LAUNCH();
+        DevBuf<int4> tiles((size_t)P.max_pair_tiles, s);
+        pair_tile_list_kernel<<<1, 256, 0, s>>>(P.K, G, g_begin.get(), tiles.get(), P.pt_count.get());
+        ASRB_CHECK_LAUNCH();
+        DevBuf<int32_t> rows;
+        if (P.mode == kModePairFinal) {
+            rows.alloc((size_t)R, s);  // R == E: position in the rare order == CSR position
+            entry_row_kernel<<<grid_for((size_t)V, 256), 256, 0, s>>>(P.d_splits, V, rows.get());
+            ASRB_CHECK_LAUNCH();
+        }
+        pair_tile_fill_kernel<<<(unsigned)P.max_pair_tiles, kTM, 0, s>>>(
+                tiles.get(), P.pt_count.get(), perm.get(), src.get(), P.mode == kModePairFinal ? rows.get() : nullptr,
+                zero_row, P.pt_slot.get(), P.pt_gidx.get(), P.pt_out.get());
+        ASRB_CHECK_LAUNCH();
+    } else {
+        ASRB_CUDA(cudaMemsetAsync(P.pt_count.get(), 0, sizeof(int), s));
+    }
+    P.d_idx = nullptr;
+    P.d_slot = nullptr;
+    P.d_splits = nullptr;
+    P.finished = true;
+}
+
+// ------------------------------------------------------------------------------------------ filters
+namespace {
+// byte offset of element (row n, half k) of a [rows x 64 halves] K-major tile with the 128-byte swizzle
+// (Swizzle<3,4,3>: the 16-byte chunk index is XORed with the row index modulo 8)
+__host__ __device__ __forceinline__ uint32_t sw128_offset(int n, int k) {
+    return (uint32_t)((n >> 3) * 1024 + (n & 7) * 128 + ((((k >> 3) ^ n) & 7) << 4) + (k & 7) * 2);
+}
+
+__global__ void __launch_bounds__(256)
+pack_filters_kernel(const float* __restrict__ W, int K, int Cin, int Cout, int col0, int ncols, int N, float scale,
+                    uint8_t* __restrict__ out) {
+    const bool c32 = Cin == 32;
+    const int chunks = c32 ? 1 : Cin / 64;
+    const int kc = c32 ? 32 : 64;
+    const size_t chunk_bytes = (size_t)(c32 ? 1 : 2) * N * 128;
+    const long long total = (long long)K * chunks * N * kc;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int kk = (int)(i % kc);
+        long long r = i / kc;
+        const int n = (int)(r % N);
+        r /= N;
+        const int c = (int)(r % chunks);
+        const int slot = (int)(r / chunks);
+        const int k = c * kc + kk;
+        const float w = n < ncols ? W[((size_t)slot * Cin + k) * Cout + col0 + n] * scale : 0.f;
+        const __half hi = __float2half_rn(w);
+        const __half lo = __float2half_rn(w - __half2float(hi));
+        uint8_t* tile = out + ((size_t)slot * chunks + c) * chunk_bytes;
+        if (c32) {  // one tile: halves 0..31 = hi, 32..63 = lo (same row layout as a 32-channel activation row)
+            *reinterpret_cast<__half*>(tile + sw128_offset(n, kk)) = hi;
+            *reinterpret_cast<__half*>(tile + sw128_offset(n, kk + 32)) = lo;
+        } else {  // hi tile, then lo tile
+            *reinterpret_cast<__half*>(tile + sw128_offset(n, kk)) = hi;
+            *reinterpret_cast<__half*>(tile + (size_t)N * 128 + sw128_offset(n, kk)) = lo;
+        }
+    }
+}
+}  // namespace
+
+static int padded_n(int ncols) { return ((ncols + 15) / 16) * 16; }
+
+size_t packed_filter_bytes(int K, int Cin, int ncols) {
+    const int N = padded_n(ncols);
+    return Cin == 32 ? (size_t)K * N * 128 : (size_t)K * (Cin / 64) * 2 * N * 128;
+}
+
+void pack_filters(const float* W, int K, int Cin, int Cout, int col0, int ncols, int scale_exp, void* out,
+                  cudaStream_t s) {
+    ASRB_REQUIRE(Cin == 32 || (Cin >= 64 && Cin % 64 == 0), "gx: in_channels must be 32 or a multiple of 64");
+    ASRB_REQUIRE(ncols >= 1 && ncols <= 256 && col0 >= 0 && col0 + ncols <= Cout, "gx: bad output column range");
+    const int N = padded_n(ncols);
+    const long long total = (long long)K * (Cin == 32 ? 1 : Cin / 64) * N * (Cin == 32 ? 32 : 64);
+    pack_filters_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, s>>>(
+            W, K, Cin, Cout, col0, ncols, N, ldexpf(1.f, scale_exp), (uint8_t*)out);
+    ASRB_CHECK_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+namespace {
+
+__device__ __forceinline__ void tma_gather4(uint32_t smem_dst, const CUtensorMap* tmap, int col, int r0, int r1, int r2,
+                                            int r3, uint32_t mbar) {
+    asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, "
+            "%4, %5, %6}], [%7];" ::"r"(smem_dst),
+            "l"(tmap), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(mbar)
+            : "memory");
+}
+
+// kind::f16 (fp16 x fp16 -> fp32), A and B K-major, M = 128
+__device__ __forceinline__ uint32_t idesc_f16(int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+            : "memory");
+}
+// K-major, 128-byte swizzle: LBO field 1 (unused), SBO = 1024 bytes (8 rows), version 1, layout type 2
+__device__ __forceinline__ uint64_t sw128_desc_base() {
+    return ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+enum { kKindStationary = 0, kKindPairBuf = 1, kKindPairFinal = 2 };
+
+struct KArgs {
+    // work
+    const int32_t* gidx;       // [steps][128]
+    const int32_t* tile_slot;  // pair kinds: slot of each tile
+    const int32_t* out_pos;    // pair kinds: destination of each lane
+    const int* num_tiles_dev;  // pair kinds
+    int num_tiles;             // stationary kind
+    int D;                     // steps per stationary tile
+    int V;
+    // input (coordinates into the tensor map)
+    int a_hi, a_lo, chunks;
+    // filters
+    const uint8_t* wp;
+    unsigned long long slot_bytes;
+    uint32_t chunk_bytes;
+    // MMA shape
+    int N, ncat, stages;
+    int G, nbuf, by_slot;  // accumulator groups per TMEM buffer, buffers, group = kernel slot (importance variant)
+    // importance variant (conv1b of SpecialSparseConv): every gathered row is weighted by imp[input row]
+    const float* imp;
+    const int32_t* rare_in;  // [R] input row of every rare entry (row-major rare order)
+    int zero_row;
+    uint32_t stage_bytes, tx_bytes;
+    // epilogue
+    float wscale;
+    const float* bias;
+    const float* norm;
+    int relu, ncols;
+    const int64_t* rare_rs;
+    const float* pairbuf;  // read (stationary)
+    float* pair_out;       // written (pair-buffer kind)
+    __half* out_h;
+    int out_pitch, out_hi, out_lo;
+    float* out_f;
+    int out_f_pitch;
+    const __half* res;
+    int res_pitch, res_hi, res_lo;
+};
+
+__device__ __forceinline__ void split_store8(__half* hi_p, __half* lo_p, const float* v, int& overflow) {
+    __align__(16) __half h[8];
+    __align__(16) __half l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float x = v[j];
+        if (fabsf(x) > 65504.f) {
+            overflow = 1;
+            x = copysignf(65504.f, x);
+        }
+        h[j] = __float2half_rn(x);
+        l[j] = __float2half_rn(x - __half2float(h[j]));
+    }
+    *reinterpret_cast<uint4*>(hi_p) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(lo_p) = *reinterpret_cast<const uint4*>(l);
+}
+
+template <bool C32, int KIND>
+__global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_constant__ CUtensorMap tmap, const KArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t bar_full[8], bar_empty[8], bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_slot;
+    const uint32_t sbase = (umma::smem_u32(smem_raw) + 1023u) & ~1023u;  // operand tiles need 1024-byte alignment
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = a.stages;
+    const int N = a.N;
+    // TMEM.  The tensor pipe TRUNCATES every addition into the fp32 accumulator (a relative bias of about
+    // -2^-24.3 per MMA, round 1's tools/tc_err.py, the same on kind::f16).  Therefore (i) the corrections
+    // A_lo B_hi + A_hi B_lo — 2^-11 of the result, their own truncation invisible — go to their own accumulator
+    // and never lengthen the main chain, and (ii) the main chain is cut into G groups (round robin over the
+    // (slot, 64-channel chunk) stages) that the epilogue adds in fp32 with round-to-nearest: G x [main N | corr N]
+    // columns per buffer, two buffers when they fit.  The importance variant uses one group per kernel slot and
+    // applies the per-row importance to each group in the epilogue (exact fp32 scaling).
+    const int G = a.G, nbuf = a.nbuf;
+    const int accw = 2 * N * G;
+    uint32_t ncols_alloc = 32;
+    while ((int)ncols_alloc < nbuf * accw) ncols_alloc <<= 1;
+    const int ntiles = KIND == kKindStationary ? a.num_tiles : *a.num_tiles_dev;
+
+    if (warp == 1) {
+        umma::tmem_alloc(&tmem_slot, ncols_alloc);
+        if (lane == 0) {
+            for (int i = 0; i < S; ++i) {
+                umma::mbar_init(&bar_full[i], 1);
+                umma::mbar_init(&bar_empty[i], 1);
+            }
+            for (int i = 0; i < 2; ++i) {
+                umma::mbar_init(&bar_tfull[i], 1);
+                umma::mbar_init(&bar_tempty[i], 4);
+            }
+            umma::fence_barrier_init();
+        }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const int steps_per_tile = KIND == kKindStationary ? a.D : 1;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (whole warp)
+        int st = 0, ph = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int sidx = 0; sidx < steps_per_tile; ++sidx) {
+                const long long step = KIND == kKindStationary ? (long long)tile * a.D + sidx : tile;
+                const int slot = KIND == kKindStationary ? sidx : a.tile_slot[tile];
+                const int4 r = *reinterpret_cast<const int4*>(a.gidx + step * kTM + lane * 4);
+                const uint8_t* wsrc = a.wp + (size_t)slot * a.slot_bytes;
+                for (int c = 0; c < a.chunks; ++c) {
+                    umma::mbar_wait(&bar_empty[st], ph ^ 1);
+                    const uint32_t stage = sbase + (uint32_t)st * a.stage_bytes;
+                    const uint32_t full = umma::smem_u32(&bar_full[st]);
+                    if (lane == 0) umma::mbar_arrive_expect_tx(&bar_full[st], a.tx_bytes);
+                    __syncwarp();
+                    tma_gather4(stage + lane * 512, &tmap, a.a_hi + c * 64, r.x, r.y, r.z, r.w, full);
+                    if (!C32) tma_gather4(stage + kATile + lane * 512, &tmap, a.a_lo + c * 64, r.x, r.y, r.z, r.w, full);
+                    if (lane == 0) {
+                        const uint32_t bdst = stage + (C32 ? 1u : 2u) * kATile;
+                        asm volatile(
+                                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(bdst),
+                                "l"(wsrc + (size_t)c * a.chunk_bytes), "r"(a.chunk_bytes), "r"(full)
+                                : "memory");
+                    }
+                    if (++st == S) {
+                        st = 0;
+                        ph ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            const uint32_t idN = idesc_f16(N), id2N = idesc_f16(2 * N);
+            const uint64_t dbase = sw128_desc_base();
+            int st = 0, ph = 0, it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int buf = it % nbuf;
+                umma::mbar_wait(&bar_tempty[buf], ((it / nbuf) & 1) ^ 1);
+                umma::tc_fence_after();
+                const uint32_t acc0 = tmem + (uint32_t)(buf * accw);
+                uint32_t started = 0;  // bit g: group g's accumulators hold this tile's data (else the MMA overwrites)
+                int sc = 0;
+                for (int sidx = 0; sidx < steps_per_tile; ++sidx) {
+                    for (int c = 0; c < a.chunks; ++c, ++sc) {
+                        umma::mbar_wait(&bar_full[st], ph);
+                        umma::tc_fence_after();
+                        const uint32_t stage = sbase + (uint32_t)st * a.stage_bytes;
+                        const int g = a.by_slot ? sidx : (sc % G);
+                        const uint32_t acc = acc0 + (uint32_t)(g * 2 * N), cor = acc + (uint32_t)N;
+                        uint32_t first = (started >> g) & 1u, firstc = first;
+                        started |= 1u << g;
+                        if (C32) {
+                            // one A tile [hi 32 | lo 32], one B tile [hi 32 | lo 32]: k-steps 0,1 = hi, 2,3 = lo
+                            const uint64_t da = dbase + (stage >> 4), db = dbase + ((stage + kATile) >> 4);
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks) {
+                                mma_f16(acc, da + 2 * ks, db + 2 * ks, idN, first);              // hi hi
+                                first = 1;
+                                mma_f16(cor, da + 2 * (ks + 2), db + 2 * ks, idN, firstc);       // lo hi
+                                firstc = 1;
+                                mma_f16(cor, da + 2 * ks, db + 2 * (ks + 2), idN, 1);            // hi lo
+                            }
+                        } else {
+                            const uint64_t dah = dbase + (stage >> 4), dal = dbase + ((stage + kATile) >> 4);
+                            const uint64_t dbh = dbase + ((stage + 2 * kATile) >> 4);
+                            const uint64_t dbl = dbh + (uint64_t)((N * 128) >> 4);
+                            if (a.ncat) {
+                                // A_hi x [B_hi | B_lo] as ONE MMA of width 2 N (the lo rows follow the hi rows, the
+                                // correction accumulator follows the main one), then A_lo x B_hi onto the corrections
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    mma_f16(acc, dah + 2 * ks, dbh + 2 * ks, id2N, first);
+                                    first = 1;
+                                    mma_f16(cor, dal + 2 * ks, dbh + 2 * ks, idN, 1);
+                                }
+                            } else {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    mma_f16(acc, dah + 2 * ks, dbh + 2 * ks, idN, first);
+                                    first = 1;
+                                    mma_f16(cor, dal + 2 * ks, dbh + 2 * ks, idN, firstc);
+                                    firstc = 1;
+                                    mma_f16(cor, dah + 2 * ks, dbl + 2 * ks, idN, 1);
+                                }
+                            }
+                        }
+                        umma::mma_commit(&bar_empty[st]);
+                        if (++st == S) {
+                            st = 0;
+                            ph ^= 1;
+                        }
+                    }
+                }
+                umma::mma_commit(&bar_tfull[buf]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int L = q * 32 + lane;
+        int overflow = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int buf = it % nbuf;
+            long long row = -1;       // output row (final kinds) / pair-buffer row
+            long long r0 = 0, r1 = 0;  // rare segment of the row
+            if (KIND == kKindStationary) {
+                const long long v = (long long)tile * kTM + L;
+                if (v < a.V) {
+                    row = v;
+                    if (a.rare_rs) {
+                        r0 = a.rare_rs[v];
+                        r1 = a.rare_rs[v + 1];
+                    }
+                }
+            } else {
+                row = a.out_pos[(size_t)tile * kTM + L];
+            }
+            const float nrm = (KIND != kKindPairBuf && a.norm && row >= 0) ? a.norm[row] : 0.f;
+            // groups of this tile that hold data; importance variant: the weight of every dense slot's row
+            const int used = a.by_slot ? steps_per_tile : min(G, steps_per_tile * a.chunks);
+            float wgt[8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) wgt[g] = 1.f;
+            if (KIND == kKindStationary && a.imp) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    if (g < used) {
+                        const int src = a.gidx[((size_t)tile * a.D + g) * kTM + L];
+                        wgt[g] = src == a.zero_row ? 0.f : a.imp[src];
+                    }
+                }
+            }
+            umma::mbar_wait(&bar_tfull[buf], (it / nbuf) & 1);
+            umma::tc_fence_after();
+            const uint32_t t_acc = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * accw);
+            for (int n0 = 0; n0 < N; n0 += 16) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                __syncwarp();  // the TMEM loads are warp-collective: reconverge after the row-dependent code below
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    if (g < used) {
+                        float m[16], c[16];
+                        umma::tmem_ld16(t_acc + g * 2 * N + n0, m);
+                        umma::tmem_ld16(t_acc + g * 2 * N + N + n0, c);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = fmaf(m[j] + c[j], wgt[g], v[j]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] *= a.wscale;
+                if (row < 0 || n0 >= a.ncols) continue;
+                if (KIND == kKindPairBuf) {
+                    float4* dst = reinterpret_cast<float4*>(a.pair_out + (size_t)row * N + n0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    continue;
+                }
+                if (KIND == kKindStationary) {
+                    for (long long p = r0; p < r1; ++p) {
+                        const float4* src = reinterpret_cast<const float4*>(a.pairbuf + (size_t)p * N + n0);
+                        const float w = a.imp ? a.imp[a.rare_in[p]] : 1.f;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 t = __ldg(src + j);
+                            v[4 * j] = fmaf(t.x, w, v[4 * j]);
+                            v[4 * j + 1] = fmaf(t.y, w, v[4 * j + 1]);
+                            v[4 * j + 2] = fmaf(t.z, w, v[4 * j + 2]);
+                            v[4 * j + 3] = fmaf(t.w, w, v[4 * j + 3]);
+                        }
+                    }
+                }
+                const int nvalid = min(16, a.ncols - n0);  // multiple of 8
+                if (KIND != kKindPairBuf && a.norm && nrm != 0.f) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] /= nrm;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (a.bias && j < nvalid) v[j] += a.bias[n0 + j];
+                    if (a.relu) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (a.res) {
+                    const __half* rh = a.res + (size_t)row * a.res_pitch + a.res_hi + n0;
+                    const __half* rl = a.res + (size_t)row * a.res_pitch + a.res_lo + n0;
+                    for (int j0 = 0; j0 < nvalid; j0 += 8) {
+                        const uint4 uh = *reinterpret_cast<const uint4*>(rh + j0);
+                        const uint4 ul = *reinterpret_cast<const uint4*>(rl + j0);
+                        const __half* hh = reinterpret_cast<const __half*>(&uh);
+                        const __half* ll = reinterpret_cast<const __half*>(&ul);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j0 + j] += __half2float(hh[j]) + __half2float(ll[j]);
+                    }
+                }
+                if (a.out_f) {
+                    float* dst = a.out_f + (size_t)row * a.out_f_pitch + n0;
+                    for (int j0 = 0; j0 < nvalid; j0 += 4)
+                        *reinterpret_cast<float4*>(dst + j0) = make_float4(v[j0], v[j0 + 1], v[j0 + 2], v[j0 + 3]);
+                } else {
+                    __half* oh = a.out_h + (size_t)row * a.out_pitch + a.out_hi + n0;
+                    __half* ol = a.out_h + (size_t)row * a.out_pitch + a.out_lo + n0;
+                    for (int j0 = 0; j0 < nvalid; j0 += 8) split_store8(oh + j0, ol + j0, v + j0, overflow);
+                }
+            }
+            umma::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(&bar_tempty[buf]);
+        }
+        if (overflow) atomicOr(&g_overflow_flag, 1);
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) umma::tmem_dealloc(tmem, ncols_alloc);
+}
+
+// ---------------------------------------------------------------- tensor map
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    if (!fn) throw Error(kCudaError, "gx: cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return fn;
+}
+
+// rows of `pitch` halves; box = 64 halves (128 bytes) x 1 row; the gather instruction moves 4 boxes
+CUtensorMap make_row_map(const H2View& x) {
+    ASRB_REQUIRE(x.p != nullptr && x.rows >= 1, "gx: null activation view");
+    ASRB_REQUIRE(((uintptr_t)x.p & 15) == 0 && (x.pitch * 2) % 16 == 0 && x.pitch >= 64,
+                 "gx: activation rows must be 16-byte aligned and at least 64 halves wide");
+    CUtensorMap m;
+    const cuuint64_t gdim[2] = {(cuuint64_t)x.pitch, (cuuint64_t)x.rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)x.pitch * 2};
+    const cuuint32_t box[2] = {64, 1};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)x.p, gdim, gstride, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error(kCudaError, "gx: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return m;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <bool C32, int KIND>
+void launch(const CUtensorMap& tmap, const KArgs& k, int grid, size_t smem, cudaStream_t s) {
+    ASRB_CUDA(cudaFuncSetAttribute(gx_conv_kernel<C32, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gx_conv_kernel<C32, KIND><<<grid, kThreads, smem, s>>>(tmap, k);
+    ASRB_CHECK_LAUNCH();
+}
+}  // namespace
+
+size_t pairbuf_floats(const Plan& P, int ncols) {
+    return P.mode == kModeStationary ? (size_t)std::max<int64_t>(P.R, 0) * padded_n(ncols) : 0;
+}
+
+void conv(const Plan& P, const ConvArgs& c, cudaStream_t s) {
+    ASRB_REQUIRE(P.finished, "gx conv: the plan is not finished");
+    const int Cin = c.x.C;
+    const bool c32 = Cin == 32;
+    ASRB_REQUIRE(c32 || (Cin >= 64 && Cin % 64 == 0), "gx conv: in_channels must be 32 or a multiple of 64");
+    ASRB_REQUIRE(c.ncols % 8 == 0 && c.ncols >= 8 && c.ncols <= 256, "gx conv: output columns must be a multiple of 8, <= 256");
+    ASRB_REQUIRE(c.x.rows == P.V_in + 1, "gx conv: the input view must hold the plan's input rows + the zero row");
+    ASRB_REQUIRE(!c32 || (c.x.hi % 64 == 0 && c.x.lo == c.x.hi + 32), "gx conv: a 32-channel input must be a plain [hi | lo] row");
+    ASRB_REQUIRE((c.out.p != nullptr) != (c.out_f32 != nullptr), "gx conv: exactly one of the h2 / fp32 outputs");
+    if (P.V == 0) return;
+    const int N = padded_n(c.ncols);
+    KArgs k{};
+    k.V = (int)P.V;
+    k.a_hi = c.x.hi;
+    k.a_lo = c.x.lo;
+    k.chunks = c32 ? 1 : Cin / 64;
+    k.wp = (const uint8_t*)c.wp;
+    k.chunk_bytes = (uint32_t)((c32 ? 1 : 2) * N * 128);
+    k.slot_bytes = (unsigned long long)k.chunks * k.chunk_bytes;
+    k.N = N;
+    ASRB_REQUIRE(N <= 128 || !c.imp, "gx conv: the importance variant needs <= 128 output columns");
+    k.ncat = (!c32 && N <= 128) ? 1 : 0;  // [B_hi | B_lo] as one operand of width 2 N <= 256
+    // accumulator groups (see the kernel): as many as fit next to a second buffer, at most 4
+    k.by_slot = 0;
+    k.nbuf = N <= 64 ? 2 : 1;
+    k.G = std::max(1, std::min(g_acc_groups > 0 ? g_acc_groups : 4, 512 / (2 * N * k.nbuf)));
+    k.zero_row = (int)P.V_in;
+    k.stage_bytes = (c32 ? 1u : 2u) * kATile + k.chunk_bytes;
+    k.tx_bytes = k.stage_bytes;
+    k.stages = (int)std::max<size_t>(2, std::min<size_t>(8, (200 * 1024) / k.stage_bytes));
+    const size_t smem = (size_t)k.stages * k.stage_bytes + 1024;
+    k.wscale = ldexpf(1.f, -c.scale_exp);
+    k.ncols = c.ncols;
+    const CUtensorMap tmap = make_row_map(c.x);
+    const bool has_rare = P.R > 0;
+    char label[96];
+    snprintf(label, sizeof(label), "gx_conv K%d %dx%d E%lld", P.K, Cin, c.ncols, (long long)P.E);
+    ProfileScope prof(label, s, 2.0 * (double)P.E * Cin * c.ncols);
+
+    auto set_final = [&](KArgs& f) {
+        f.bias = c.bias;
+        f.norm = c.norm;
+        f.relu = c.relu;
+        if (c.out.p) {
+            ASRB_REQUIRE(c.out.hi % 8 == 0 && c.out.lo % 8 == 0 && c.out.pitch % 8 == 0, "gx conv: output view alignment");
+            f.out_h = c.out.p;
+            f.out_pitch = c.out.pitch;
+            f.out_hi = c.out.hi;
+            f.out_lo = c.out.lo;
+        } else {
+            ASRB_REQUIRE(c.out_f32_pitch % 4 == 0 && c.out_f32_col % 4 == 0, "gx conv: fp32 output alignment");
+            f.out_f = c.out_f32 + c.out_f32_col;
+            f.out_f_pitch = c.out_f32_pitch;
+        }
+        if (c.res.p) {
+            f.res = c.res.p;
+            f.res_pitch = c.res.pitch;
+            f.res_hi = c.res.hi;
+            f.res_lo = c.res.lo;
+        }
+    };
+
+    if (has_rare) {
+        KArgs r = k;
+        r.gidx = P.pt_gidx.get();
+        r.tile_slot = P.pt_slot.get();
+        r.out_pos = P.pt_out.get();
+        r.num_tiles_dev = P.pt_count.get();
+        const int grid = std::min(P.max_pair_tiles, sm_count());
+        if (P.mode == kModePairFinal) {
+            set_final(r);
+            if (c32) launch<true, kKindPairFinal>(tmap, r, grid, smem, s);
+            else launch<false, kKindPairFinal>(tmap, r, grid, smem, s);
+        } else {
+            ASRB_REQUIRE(c.pairbuf != nullptr, "gx conv: pair buffer missing");
+            r.pair_out = c.pairbuf;
+            if (c32) launch<true, kKindPairBuf>(tmap, r, grid, smem, s);
+            else launch<false, kKindPairBuf>(tmap, r, grid, smem, s);
+        }
+    }
+    if (P.mode == kModeStationary) {
+        KArgs o = k;
+        o.gidx = P.gidx.get();
+        o.num_tiles = (int)P.T;
+        o.D = P.D;
+        o.rare_rs = has_rare ? P.rare_rs.get() : nullptr;
+        o.pairbuf = c.pairbuf;
+        if (c.imp) {  // one accumulator group per dense slot, weighted in the epilogue
+            ASRB_REQUIRE(P.D <= 8 && 2 * N * P.D <= 512, "gx conv: importance variant: too many columns");
+            o.imp = c.imp;
+            o.rare_in = P.rare_in.get();
+            o.by_slot = 1;
+            o.G = P.D;
+            o.nbuf = 2 * N * P.D * 2 <= 512 ? 2 : 1;
+        }
+        set_final(o);
+        const int grid = (int)std::min<int64_t>(P.T, sm_count());
+        if (c32) launch<true, kKindStationary>(tmap, o, grid, smem, s);
+        else launch<false, kKindStationary>(tmap, o, grid, smem, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ format helpers
+namespace {
+// 8 channels per thread
+__global__ void __launch_bounds__(256)
+from_f32_kernel(const float* __restrict__ x, long long V, int C, int ldx, const float* __restrict__ row_scale,
+                __half* __restrict__ out, int pitch, int hi, int lo) {
+    const int c8 = C >> 3;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= V * c8) return;
+    const long long row = i / c8;
+    const int col = (int)(i - row * c8) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(x + row * ldx + col);
+    const float4 b = *reinterpret_cast<const float4*>(x + row * ldx + col + 4);
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (row_scale) {
+        const float s = row_scale[row];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= s;
+    }
+    int overflow = 0;
+    split_store8(out + row * pitch + hi + col, out + row * pitch + lo + col, v, overflow);
+    if (overflow) atomicOr(&g_overflow_flag, 1);
+}
+
+__global__ void __launch_bounds__(256)
+to_f32_kernel(const __half* __restrict__ x, long long V, int C, int pitch, int hi, int lo, const float* __restrict__ row_scale,
+              float* __restrict__ out_f, int ldo, __half* __restrict__ out_h, int opitch, int ohi, int olo) {
+    const int c8 = C >> 3;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= V * c8) return;
+    const long long row = i / c8;
+    const int col = (int)(i - row * c8) * 8;
+    const uint4 uh = *reinterpret_cast<const uint4*>(x + row * pitch + hi + col);
+    const uint4 ul = *reinterpret_cast<const uint4*>(x + row * pitch + lo + col);
+    const __half* hh = reinterpret_cast<const __half*>(&uh);
+    const __half* ll = reinterpret_cast<const __half*>(&ul);
+    float v[8];
+    const float s = row_scale ? row_scale[row] : 1.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (__half2float(hh[j]) + __half2float(ll[j])) * s;
+    if (out_f) {
+        *reinterpret_cast<float4*>(out_f + row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(out_f + row * ldo + col + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+        int overflow = 0;
+        split_store8(out_h + row * opitch + ohi + col, out_h + row * opitch + olo + col, v, overflow);
+        if (overflow) atomicOr(&g_overflow_flag, 1);
+    }
+}
+}  // namespace
+
+static void zero_last_row(const H2View& v, cudaStream_t s) {
+    // only the columns of this view (hi and lo parts); a slice of a shared buffer leaves the rest alone
+    ASRB_CUDA(cudaMemsetAsync(v.p + (size_t)(v.rows - 1) * v.pitch + v.hi, 0, (size_t)v.C * 2, s));
+    ASRB_CUDA(cudaMemsetAsync(v.p + (size_t)(v.rows - 1) * v.pitch + v.lo, 0, (size_t)v.C * 2, s));
+}
+
+void from_f32(const float* x, int64_t V, int C, int ldx, const float* row_scale, H2View out, cudaStream_t s) {
+    ASRB_REQUIRE(C % 8 == 0 && ldx % 4 == 0 && out.C == C && out.rows == V + 1, "gx from_f32: bad shapes");
+    if (V > 0) {
+        from_f32_kernel<<<grid_for((size_t)V * (C / 8), 256), 256, 0, s>>>(x, V, C, ldx, row_scale, out.p, out.pitch, out.hi,
+                                                                          out.lo);
+        ASRB_CHECK_LAUNCH();
+    }
+    zero_last_row(out, s);
+}
+
+void to_f32(H2View x, int64_t V, float* out, int ldo, cudaStream_t s) {
+    ASRB_REQUIRE(x.C % 8 == 0 && ldo % 4 == 0, "gx to_f32: bad shapes");
+    if (V == 0) return;
+    to_f32_kernel<<<grid_for((size_t)V * (x.C / 8), 256), 256, 0, s>>>(x.p, V, x.C, x.pitch, x.hi, x.lo, nullptr, out, ldo,
+                                                                      nullptr, 0, 0, 0);
+    ASRB_CHECK_LAUNCH();
+}
+
+void scale_rows(H2View x, int64_t V, const float* row_scale, H2View out, cudaStream_t s) {
+    ASRB_REQUIRE(x.C % 8 == 0 && out.C == x.C && out.rows == V + 1, "gx scale_rows: bad shapes");
+    if (V > 0) {
+        to_f32_kernel<<<grid_for((size_t)V * (x.C / 8), 256), 256, 0, s>>>(x.p, V, x.C, x.pitch, x.hi, x.lo, row_scale,
+                                                                          nullptr, 0, out.p, out.pitch, out.hi, out.lo);
+        ASRB_CHECK_LAUNCH();
+    }
+    zero_last_row(out, s);
+}
+
+int overflow_flag_read_and_clear(cudaStream_t s) {
+    int v = 0, z = 0;
+    ASRB_CUDA(cudaMemcpyFromSymbolAsync(&v, g_overflow_flag, sizeof(int), 0, cudaMemcpyDeviceToHost, s));
+    ASRB_CUDA(cudaMemcpyToSymbolAsync(g_overflow_flag, &z, sizeof(int), 0, cudaMemcpyHostToDevice, s));
+    ASRB_CUDA(cudaStreamSynchronize(s));
+    return v;
+}
+
+}  // namespace gx
+}  // namespace asrb

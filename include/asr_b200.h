@@ -163,6 +163,47 @@ int asr_invert_neighbors_list(int64_t num_points, const int32_t* d_inp_neighbors
                               const void* d_inp_attributes, int attribute_bytes, int32_t* d_neighbors_index,
                               int64_t* d_neighbors_row_splits, void* d_neighbors_attributes, void* stream);
 
+/* ---------------------------------------------------------------- U-Net convolutions on split-half activations ("gx")
+ * The fast path of model.unet (reference UNet5.unet, net_definitions_torch.py:535-638; every SparseConvBlock /
+ * SparseConvTransitionBlock conv :123-387 = SpecialSparseConv.forward, models/common_torch.py:95-148, i.e. Open3D
+ * `sparse_conv` + bias + ReLU): the same convolution as asr_sparse_conv for activations that stay on the device
+ * between layers in a split-half format — a [V, C] tensor is stored as rows of `pitch` fp16 values holding hi =
+ * fp16(x) at columns [hi, hi + C) and lo = fp16(x - hi) at [lo, lo + C) (4 bytes per element like fp32); buffers
+ * have V + 1 rows, the last one all zero.  csrc/spconv_gx.cu describes the kernel (TMA row gather, fp16 hi/lo
+ * tcgen05 MMAs into TMEM, output-stationary dense slots + pair-major rare slots, fused epilogue).
+ * mode 0: within-grid (K = 55) and down (K = 9, inverted up table) tables; mode 1: up tables (one entry per row).
+ * _plan_begin queues the counting kernels, _plan_finish (one host synchronisation, shared by all plans begun
+ * before it) completes the plan and returns the number of rare entries (pair-buffer rows). */
+typedef struct asr_gx_plan asr_gx_plan;
+int asr_gx_plan_begin(const int32_t* d_neighbors_index, const uint8_t* d_neighbors_kernel_index,
+                      const int64_t* d_neighbors_row_splits, int64_t num_out, int64_t num_in, int64_t num_entries,
+                      int kernel_size, int mode, void* stream, asr_gx_plan** out);
+int asr_gx_plan_finish(asr_gx_plan* plan, void* stream, int64_t* num_rare);
+void asr_gx_plan_destroy(asr_gx_plan* plan);
+/* filters [K, Cin, Cout] fp32 -> fp16 hi/lo of W * 2^scale_exp for output columns [col0, col0 + ncols) in the
+ * kernel's shared-memory image; Cin = 32 or a multiple of 64, ncols a multiple of 8, <= 256 */
+int64_t asr_gx_packed_filters_bytes(int kernel_size, int in_channels, int ncols);
+int asr_gx_pack_filters(const float* d_filters, int kernel_size, int in_channels, int out_channels, int col0, int ncols,
+                        int scale_exp, void* d_packed, void* stream);
+/* fp32 [V, C] (row stride ldx) (* row_scale[row] if given) -> split-half view; also zeroes the view's zero row */
+int asr_gx_from_f32(const float* d_x, int64_t num_rows, int channels, int ldx, const float* d_row_scale, void* d_out,
+                    int out_pitch, int out_hi, int out_lo, void* stream);
+int asr_gx_to_f32(const void* d_x, int64_t num_rows, int channels, int pitch, int hi, int lo, float* d_out, int ldo,
+                  void* stream);
+/* out = row_scale[row] * x, both split-half (the importance-weighted copy of SpecialSparseConv's conv1b input) */
+int asr_gx_scale_rows(const void* d_x, int64_t num_rows, int channels, int pitch, int hi, int lo,
+                      const float* d_row_scale, void* d_out, int out_pitch, int out_hi, int out_lo, void* stream);
+/* out[o, 0:ncols] = act(sum_n (imp[idx_n]) x[idx_n] @ W[slot_n] (/ norm[o] where != 0) + bias) (+ residual[o]);
+ * d_imp (may be NULL; ncols <= 128): importance per INPUT row, applied in fp32 in the epilogue; exactly one of
+ * d_out_h2 (split-half view) / d_out_f32 (row stride out_f32_pitch floats) is given; d_pairbuf = scratch of
+ * num_rare * roundup(ncols, 16) floats (mode 0 plans with rare entries) */
+int asr_gx_conv(const asr_gx_plan* plan, const void* d_x, int in_channels, int x_pitch, int x_hi, int x_lo,
+                const void* d_packed, int ncols, int scale_exp, const float* d_bias, int relu, const float* d_norm,
+                const float* d_imp, const void* d_res, int res_pitch, int res_hi, int res_lo, void* d_out_h2, int out_pitch, int out_hi,
+                int out_lo, float* d_out_f32, int out_f32_pitch, float* d_pairbuf, void* stream);
+/* 1 if a conversion to the split-half format saturated (|x| > 65504) since the last call; synchronises */
+int asr_gx_overflow(void* stream, int* flag);
+
 /* ---------------------------------------------------------------- decoder MLP
  * replaces UNet5.decode / decode_with_gradient, net_definitions_torch.py:655-686.
  * weights in torch.nn.Linear layout: w1 [32,35], b1 [32], w2 [32,32], b2 [32], w3 [2,32].

@@ -160,7 +160,11 @@ void add_with_ancestors(Tree& t, Key k) {
     if (k == 0) t.groups.insert(0);  // INVALID_KEY inserted by octree.cpp:257
 }
 
-// octree.cpp:152-206.  Sequential sweep over a worklist in ascending key order.
+// octree.cpp:152-206.  Sequential sweep: the first pass visits the first-sibling keys in the
+// iteration order of the reference's hash map — ascending keys for the pinned oracle (std::map
+// stand-in, oracle/shim/libcuckoo) — and every later pass visits the groups created by the previous
+// one in creation order (keys_to_process2, :195-197).  The leaf test (:171) sees the nodes inserted
+// so far, so the order is part of the algorithm.
 void balance(Tree& t) {
     static const int dirs[6][3] = {{-1, 0, 0}, {0, -1, 0}, {0, 0, -1},
                                    {1, 0, 0},  {0, 1, 0},  {0, 0, 1}};
@@ -184,7 +188,6 @@ void balance(Tree& t) {
         }
         work.swap(next);
         next.clear();
-        std::sort(work.begin(), work.end());
     }
 }
 

@@ -11,7 +11,10 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_PATH = os.path.join(_HERE, "_ref", "libasr_ref.so")
+# ASR_REF_VARIANT=unordered loads the build whose hash-map stand-in iterates in std::unordered_map order
+# (only for the order-dependence experiment, oracle/shim/libcuckoo/cuckoohash_map.hh)
+_PATH = os.path.join(_HERE, "_ref", "libasr_ref_unordered.so" if os.environ.get("ASR_REF_VARIANT") == "unordered"
+                     else "libasr_ref.so")
 
 _lib = None
 

@@ -1,16 +1,28 @@
 // Test infrastructure only (oracle/): stand-in for libcuckoo's concurrent hash
 // map (absent in this image) with just the member functions the reference
-// octree code calls.  Backed by std::unordered_map; single-threaded use only.
-// The reference results do not depend on iteration order.
+// octree code calls; single-threaded use only.
+//
+// Iteration order matters: Octree::BalanceFaces (octree.cpp:152-206) tests "is this key still a
+// leaf?" while it inserts nodes, so its result depends on the order in which the first pass visits
+// the map (found in round 2: at 10 M points 17 of 3.6 M leaves differ between two orders; every
+// cloud up to a few million points gives identical trees).  libcuckoo's own order (bucket index of
+// the hashed key after its growth history) cannot be reproduced without the library, so the pinned
+// oracle uses a DEFINED order: std::map, ascending keys (the default here).  -DASR_SHIM_UNORDERED_MAP
+// selects std::unordered_map (round 1's stand-in) for the order-dependence experiment.
 #pragma once
 #include <cstddef>
+#include <map>
 #include <unordered_map>
 
 namespace libcuckoo {
 
 template <class K, class V>
 class cuckoohash_map {
+#ifdef ASR_SHIM_UNORDERED_MAP
     typedef std::unordered_map<K, V> Store;
+#else
+    typedef std::map<K, V> Store;
+#endif
     Store store_;
 
 public:

@@ -142,6 +142,26 @@ def test_asrtool_ply_to_ply(tmp_path):
     assert asrtool.main(["--version"]) == 0 and asrtool.main([]) == 1
 
 
+_INVERT_SCRIPT = None
+
+
+def _invert_script():
+    """The reference wraps the call in a scripted function so that the voxel count stays a run-time value under
+    torch.jit.trace (net_definitions_torch.py:22-36); a plain `.shape[0]` would be baked into the trace."""
+    global _INVERT_SCRIPT
+    if _INVERT_SCRIPT is None:
+        import open3d.ml.torch as ml3d
+
+        @torch.jit.script
+        def invert_neighbors_list_script(num_points_tensor, neighbors_index, neighbors_row_splits, neighbors_kernel_index):
+            ans = ml3d.ops.invert_neighbors_list(num_points_tensor.shape[0], neighbors_index, neighbors_row_splits,
+                                                 neighbors_kernel_index)
+            return ans
+
+        _INVERT_SCRIPT = invert_neighbors_list_script
+    return _INVERT_SCRIPT
+
+
 class _MiniRefNet(torch.nn.Module):
     """A two-stage network that calls the shim exactly the way the reference's layers do
     (SpecialSparseConv.forward common_torch.py:124-148, CConvAggregationBlock.forward
@@ -177,13 +197,12 @@ class _MiniRefNet(torch.nn.Module):
         return f, nimp
 
     def unet(self, feats1, d):
-        import open3d.ml.torch as ml3d
         x, imp = feats1
         y, imp1 = self._sconv(self.k_nb, x, d["neighbors_index0"], d["neighbors_kernel_index0"],
                               d["neighbors_row_splits0"], imp, True)
         y = F.relu(y + self.bias)
-        ans = ml3d.ops.invert_neighbors_list(d["voxel_centers1"].shape[0], d["up_neighbors_index0"],
-                                             d["up_neighbors_row_splits0"], d["up_neighbors_kernel_index0"])
+        ans = _invert_script()(d["voxel_centers1"], d["up_neighbors_index0"], d["up_neighbors_row_splits0"],
+                               d["up_neighbors_kernel_index0"])
         z, _ = self._sconv(self.k_down, y, ans.neighbors_index, ans.neighbors_attributes, ans.neighbors_row_splits,
                            imp1, False)
         return y, z
