@@ -23,6 +23,7 @@ SIGNATURES = {
     "asr_last_error": (C.c_char_p, []),
     "asr_kernel_launches": (_i64, []),
     "asr_set_option": (_i32, [C.c_char_p, _i32]),
+    "asr_pool_stats": (_i32, [_pi64, _pi64, _pi64]),
     "asr_profile_enable": (None, [_i32]),
     "asr_profile_reset": (None, []),
     "asr_profile_count": (_i32, []),
@@ -51,7 +52,7 @@ SIGNATURES = {
     "asr_packed_conv_filters_size": (_i64, [_i32, _i32, _i32]),
     "asr_pack_conv_filters": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "asr_sparse_conv": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
-    "asr_gx_plan_begin": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _pp]),
+    "asr_gx_plan_begin": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _pp]),
     "asr_gx_plan_finish": (_i32, [_vp, _vp, _pi64]),
     "asr_gx_plan_destroy": (None, [_vp]),
     "asr_gx_packed_filters_bytes": (_i64, [_i32, _i32, _i32]),
@@ -62,6 +63,10 @@ SIGNATURES = {
     "asr_gx_conv": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32,
                            _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp]),
     "asr_gx_overflow": (_i32, [_vp, C.POINTER(C.c_int)]),
+    "asr_shard_positions": (_i32, [_vp, _i64, _vp, _vp]),
+    "asr_shard_owner": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp]),
+    "asr_shard_need_mask": (_i32, [_vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp]),
+    "asr_shard_push": (_i32, [_vp, _i32, _i32, _i64, _i64, _vp, _i32, _i32, _vp, _i64, _vp, _vp]),
     "asr_reduce_subarrays_sum": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "asr_invert_neighbors_list": (_i32, [_i64, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _vp]),
     "asr_decode": (_i32, [_vp, _vp, _i64] + [_vp] * 9),
@@ -81,6 +86,13 @@ SIGNATURES = {
 }
 
 _lib = None
+
+
+def pool_stats():
+    """(reserved, used, release threshold) bytes of the library's stream-ordered memory pool"""
+    a, b, c = _i64(0), _i64(0), _i64(0)
+    check(lib().asr_pool_stats(C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value
 
 
 def lib():

@@ -78,18 +78,23 @@ MODE_STATIONARY, MODE_PAIR_FINAL = 0, 1
 class Plan:
     """Gather tables / pair tiles of one neighbour table (begin now, finish() after all plans were begun)."""
 
-    def __init__(self, idx, slot, row_splits, num_in, kernel_size, mode):
+    def __init__(self, idx, slot, row_splits, num_in, kernel_size, mode, rows=None):
+        """rows (int32, ascending): build the plan for these table rows only (this rank's rows of a sharded level);
+        the convolution then writes exactly these rows of its (full-size) output."""
         self.idx = ops._cuda(idx, torch.int32, "neighbors_index")
         self.slot = ops._cuda(slot, torch.uint8, "neighbors_kernel_index")
         self.row_splits = ops._cuda(row_splits, torch.int64, "neighbors_row_splits")
-        self.num_out = self.row_splits.shape[0] - 1
+        self.rows = None if rows is None else ops._cuda(rows, torch.int32, "rows")
+        self.table_rows = self.row_splits.shape[0] - 1
+        self.num_out = self.table_rows if rows is None else int(self.rows.shape[0])
         self.num_in = int(num_in)
         self.kernel_size = int(kernel_size)
         self.mode = mode
         self.num_rare = None
         self._h = C.c_void_p(0)
         check(lib().asr_gx_plan_begin(_ptr(self.idx), _ptr(self.slot), _ptr(self.row_splits), self.num_out, self.num_in,
-                                      self.idx.shape[0], self.kernel_size, mode, _stream(), C.byref(self._h)))
+                                      self.idx.shape[0], self.kernel_size, mode, _ptr(self.rows), _stream(),
+                                      C.byref(self._h)))
 
     def finish(self):
         if self.num_rare is None:
@@ -139,7 +144,7 @@ class Scratch:
         return self.buf
 
 
-def conv(plan, x, filt, relu=True, norm=None, res=None, out=None, out_f32=None, scratch=None, imp=None):
+def conv(plan, x, filt, relu=True, norm=None, res=None, out=None, out_f32=None, scratch=None, imp=None, alloc=None):
     """out[:, 0:ncols] = act(sparse_conv(x) (/ norm) + bias) (+ res); `out` an H2 view or `out_f32` a float32
     [V, ncols] tensor.  imp: importance of every INPUT row (weights each gathered row, in fp32 in the epilogue)."""
     if isinstance(filt, (list, tuple)):
@@ -147,7 +152,7 @@ def conv(plan, x, filt, relu=True, norm=None, res=None, out=None, out_f32=None, 
         # its main accumulation chain split over two TMEM accumulators, see the kernel)
         total = sum(f.ncols for f in filt)
         if out is None and out_f32 is None:
-            out = H2.empty(plan.num_out, total, x.buf.device)
+            out = (alloc or H2.empty)(plan.table_rows, total, x.buf.device)
         account, ops.ACCOUNT = ops.ACCOUNT, None
         try:
             for f in filt:
@@ -163,12 +168,14 @@ def conv(plan, x, filt, relu=True, norm=None, res=None, out=None, out_f32=None, 
         return out if out is not None else out_f32
     if x.C != filt.Cin or plan.kernel_size != filt.K or x.V != plan.num_in:
         raise ValueError("gx.conv: shapes of the input / filters / plan do not match")
+    if filt.ncols > 128:
+        raise ValueError("gx.conv: more than 128 output columns per call — pack the bank with gx.filter_bank")
     plan.finish()
     npad = (filt.ncols + 15) // 16 * 16
     need = plan.num_rare * npad
     pb = (scratch or Scratch()).get(need, x.buf.device)
     if out is None and out_f32 is None:
-        out = H2.empty(plan.num_out, filt.ncols, x.buf.device)
+        out = (alloc or H2.empty)(plan.table_rows, filt.ncols, x.buf.device)
     rp = res.args() if res is not None else (C.c_void_p(0), 0, 0, 0)
     op = out.args() if out is not None else (C.c_void_p(0), 0, 0, 0)
     check(lib().asr_gx_conv(plan._h, _ptr(x.buf), x.C, x.pitch, x.hi, x.lo, _ptr(filt.data), filt.ncols, filt.scale_exp,
@@ -216,13 +223,28 @@ def _block_filters(block):
     return block._gx
 
 
-def run_block(block, x, plan, importance, scratch, out=None, out_f32=None, res=None):
+class LocalContext:
+    """Where the U-Net's buffers live and what happens after a convolution.  Single GPU: torch allocations, nothing
+    to do.  shard_gx.ShardContext allocates from a symmetric arena and pushes the halo rows to the peers."""
+
+    def empty(self, V, C_, device):
+        return H2.empty(V, C_, device)
+
+    def done(self, view, level):
+        pass
+
+    def plans(self, input_dict, levels):
+        return build_plans(input_dict, levels)
+
+
+def run_block(block, x, plan, importance, scratch, out=None, out_f32=None, res=None, ctx=None, level=None):
     """model._Block.run on H2 activations.  `out` / `out_f32` / `res` apply to the block's LAST convolution."""
+    ctx = ctx or LocalContext()
     first, firstb, rest = _block_filters(block)
     out_imp = None
     last = not rest
     y = conv(plan, x, first, out=out if last else None, out_f32=out_f32 if last else None,
-             res=res if last else None, scratch=scratch)
+             res=res if last else None, scratch=scratch, alloc=ctx.empty)
     if block.split:
         # conv1b (common_torch.py:124-142 with normalize=True): importance-weighted input, divided by the summed
         # importance of the row; lands in the last 8 channels of the block's first activation (:283,378)
@@ -231,10 +253,14 @@ def run_block(block, x, plan, importance, scratch, out=None, out_f32=None, res=N
         if y is out_f32 and out_f32 is not None:
             raise ValueError("a split block cannot end in an fp32 output")
         conv(plan, x, firstb, norm=out_imp, imp=importance, out=y.slice(col, NORMALIZED_CHANNELS), scratch=scratch)
+    if isinstance(y, H2):
+        ctx.done(y, level)
     for i, f in enumerate(rest):
         last = i == len(rest) - 1
         y = conv(plan, y, f, out=out if last else None, out_f32=out_f32 if last else None, res=res if last else None,
-                 scratch=scratch)
+                 scratch=scratch, alloc=ctx.empty)
+        if isinstance(y, H2):
+            ctx.done(y, level)
     return y, out_imp
 
 
@@ -262,16 +288,18 @@ def build_plans(input_dict, levels):
     return P
 
 
-def unet(net, feats1, input_dict, taps=None):
-    """UNet5.unet (:535-638) for `net.octree_levels` grids on the gx kernels.  Returns code [V0, 32] float32."""
+def unet(net, feats1, input_dict, taps=None, ctx=None, x0=None, code=None):
+    """UNet5.unet (:535-638) for `net.octree_levels` grids on the gx kernels.  Returns code [V0, 32] float32.
+    ctx: buffer / halo context (default: single GPU); x0: the aggregated features already in split-half form."""
     from .model import enc_channels
+    ctx = ctx or LocalContext()
     L = net.octree_levels
-    P = build_plans(input_dict, L)
+    P = ctx.plans(input_dict, L)
     V = P["V"]
     feats, imp = feats1
-    dev = feats.device
+    dev = imp.device
     scratch = Scratch()
-    x = from_f32(feats)
+    x = x0 if x0 is not None else from_f32(feats)
     # encoder: the output of every level except the deepest is the second part of that level's decoder input
     # (torch.cat([up, skip]), :607-631), so it is written straight into that buffer
     cat = [None] * L
@@ -279,29 +307,29 @@ def unet(net, feats1, input_dict, taps=None):
     for l in range(L):
         C_l = enc_channels(l)
         if l >= 1:
-            x, imp = run_block(net._down(l), x, P["down"][l - 1], imp, scratch)
+            x, imp = run_block(net._down(l), x, P["down"][l - 1], imp, scratch, ctx=ctx, level=l)
         block = net.sparseconv_encblock0 if l == 0 else getattr(net, "sparseconv_encblock%d" % l)
         out = None
         if 1 <= l <= L - 2:
-            cat[l] = H2.empty(V[l], 256 + C_l, dev)
+            cat[l] = ctx.empty(V[l], 256 + C_l, dev)
             out = cat[l].slice(256, C_l)
-        x, imp = run_block(block, x, P["nb"][l], imp, scratch, out=out)
+        x, imp = run_block(block, x, P["nb"][l], imp, scratch, out=out, ctx=ctx, level=l)
         skips[l] = x
     if taps is not None:
         taps.update({"enc%d" % l: s.to_f32() for l, s in enumerate(skips)})
-    code = None
     for l in range(L - 2, -1, -1):
         up = getattr(net, "sparseconv_up%d" % l)
         dec = getattr(net, "sparseconv_decblock%d" % l)
         if l >= 1:
-            run_block(up, x, P["up"][l], None, scratch, out=cat[l].slice(0, 256))
-            x, _ = run_block(dec, cat[l], P["nb"][l], None, scratch)
+            run_block(up, x, P["up"][l], None, scratch, out=cat[l].slice(0, 256), ctx=ctx, level=l)
+            x, _ = run_block(dec, cat[l], P["nb"][l], None, scratch, ctx=ctx, level=l)
             if taps is not None:
                 taps["dec%d" % l] = x.to_f32()
         else:
-            x, _ = run_block(up, x, P["up"][0], None, scratch, res=skips[0])  # feats20 + feats2 (:633-634)
-            code = torch.empty((V[0], 32), dtype=torch.float32, device=dev)
-            run_block(dec, x, P["nb"][0], None, scratch, out_f32=code)
+            x, _ = run_block(up, x, P["up"][0], None, scratch, res=skips[0], ctx=ctx, level=0)  # feats20 + feats2 (:633-634)
+            if code is None:
+                code = torch.empty((V[0], 32), dtype=torch.float32, device=dev)
+            run_block(dec, x, P["nb"][0], None, scratch, out_f32=code, ctx=ctx, level=0)
             if taps is not None:
                 taps["dec0"] = code
     return code

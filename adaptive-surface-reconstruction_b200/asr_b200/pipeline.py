@@ -138,7 +138,8 @@ def _as_host_tensor(a):
     return torch.from_numpy(np.ascontiguousarray(a, np.float32))
 
 
-def reconstruct_vertices_host(model, points, normals, radii, bb_min=None, bb_max=None, pinned_out=False, **kw):
+def reconstruct_vertices_host(model, points, normals, radii, bb_min=None, bb_max=None, pinned_out=False, shard_ctx=None,
+                              **kw):
     """Same path with HOST buffers in and out (numpy arrays or CPU tensors, ideally pinned): H2D of
     the cloud, the device path, D2H of the vertices and SDF values.  This is the call the `e2e`
     benchmark number times.  The normals (first needed by the aggregation, after the octree and the
@@ -160,7 +161,12 @@ def reconstruct_vertices_host(model, points, normals, radii, bb_min=None, bb_max
         ready = torch.cuda.Event()
         ready.record(_COPY_STREAM)
     n.record_stream(main)
-    out = reconstruct_vertices(model, p, n, r, bb_min, bb_max, normals_ready=ready, **kw)
+    if shard_ctx is not None:  # multi-GPU: every rank uploads the cloud and runs its share (shard_gx.py)
+        from . import shard_gx
+        main.wait_event(ready)
+        out = shard_gx.reconstruct_vertices(model, shard_ctx, p, n, r, bb_min, bb_max, **kw)
+    else:
+        out = reconstruct_vertices(model, p, n, r, bb_min, bb_max, normals_ready=ready, **kw)
     v, s = _to_host(out["vertices"], "vertices"), _to_host(out["values"], "values")
     t = _to_host(out["triangles"], "triangles") if "triangles" in out else None
     main.synchronize()

@@ -34,6 +34,12 @@ size_t packed_weights_floats(int K, int N);
 void pack_weights(const float* W, int K, int N, float* out, cudaStream_t s);
 void dense_gemm_tf32x3(const float* A, int64_t M, int K, int lda, const float* Wp, int N, const float* bias, int relu,
                        float* D, int ldd, cudaStream_t s);
+void shard_positions(const Key* keys, int64_t V, unsigned long long* pos, cudaStream_t s);
+void shard_owner(const Key* keys, int64_t V, const unsigned long long* thr, int nthr, uint8_t* owner, cudaStream_t s);
+void shard_need_mask(const int64_t* splits, const int32_t* idx, int64_t V_out, const uint8_t* owner_out,
+                     const uint8_t* owner_in, int me, uint32_t* mask, cudaStream_t s);
+void shard_push(void* const* peer_base, int world, int me, int64_t offset, int64_t pitch, const int* seg_off, int nseg,
+                int seg_len, const int32_t* rows, int64_t nrows, const uint32_t* mask, cudaStream_t s);
 void profile_set(bool on);
 void profile_reset();
 int profile_count();
@@ -108,9 +114,32 @@ int asr_set_option(const char* name, int value) {
         else if (std::string(name) == "conv_row_block_shift") sparse_conv_row_block_shift(value);
         else if (std::string(name) == "tc_ntile") sparse_conv_tc_ntile(value);
         else if (std::string(name) == "gx_acc_groups") gx::set_acc_groups(value);
+        else if (std::string(name) == "gx_tma_gather") gx::set_tma_gather(value);
         else if (std::string(name) == "tc_stages") sparse_conv_tc_tune(value, 0);
         else if (std::string(name) == "tc_row_groups") sparse_conv_tc_tune(0, value);
         else throw Error(kInvalidArgument, std::string("unknown option: ") + name);
+    });
+}
+
+int asr_pool_stats(int64_t* reserved_bytes, int64_t* used_bytes, int64_t* release_threshold) {
+    return guarded([&] {
+        int dev = 0;
+        ASRB_CUDA(cudaGetDevice(&dev));
+        cudaMemPool_t pool;
+        ASRB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t v = 0;
+        if (reserved_bytes) {
+            ASRB_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &v));
+            *reserved_bytes = (int64_t)v;
+        }
+        if (used_bytes) {
+            ASRB_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &v));
+            *used_bytes = (int64_t)v;
+        }
+        if (release_threshold) {
+            ASRB_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &v));
+            *release_threshold = v > (uint64_t)INT64_MAX ? INT64_MAX : (int64_t)v;
+        }
     });
 }
 
@@ -329,12 +358,13 @@ int asr_sparse_conv(const asr_conv_plan* plan, const float* filters, const float
     });
 }
 int asr_gx_plan_begin(const int32_t* idx, const uint8_t* slot, const int64_t* splits, int64_t num_out, int64_t num_in,
-                      int64_t num_entries, int kernel_size, int mode, void* stream, asr_gx_plan** out) {
+                      int64_t num_entries, int kernel_size, int mode, const int32_t* row_map, void* stream,
+                      asr_gx_plan** out) {
     return guarded([&] {
         ASRB_REQUIRE(out, "null argument");
         ASRB_REQUIRE(num_out >= 0 && num_in >= 0 && num_entries >= 0, "negative size");
         auto h = std::make_unique<asr_gx_plan>();
-        gx::plan_begin(h->p, idx, slot, splits, num_out, num_in, num_entries, kernel_size, mode, S(stream));
+        gx::plan_begin(h->p, idx, slot, splits, num_out, num_in, num_entries, kernel_size, mode, row_map, S(stream));
         *out = h.release();
     });
 }
@@ -409,6 +439,28 @@ int asr_gx_conv(const asr_gx_plan* plan, const void* d_x, int in_channels, int x
         gx::conv(plan->p, a, S(stream));
     });
 }
+int asr_shard_positions(const uint64_t* d_keys, int64_t num_voxels, uint64_t* d_pos, void* stream) {
+    return guarded([&] { shard_positions((const Key*)d_keys, num_voxels, (unsigned long long*)d_pos, S(stream)); });
+}
+int asr_shard_owner(const uint64_t* d_keys, int64_t num_voxels, const uint64_t* d_thresholds, int num_thresholds,
+                    uint8_t* d_owner, void* stream) {
+    return guarded([&] {
+        shard_owner((const Key*)d_keys, num_voxels, (const unsigned long long*)d_thresholds, num_thresholds, d_owner,
+                    S(stream));
+    });
+}
+int asr_shard_need_mask(const int64_t* d_row_splits, const int32_t* d_index, int64_t num_out, const uint8_t* d_owner_out,
+                        const uint8_t* d_owner_in, int rank, uint32_t* d_mask, void* stream) {
+    return guarded([&] { shard_need_mask(d_row_splits, d_index, num_out, d_owner_out, d_owner_in, rank, d_mask, S(stream)); });
+}
+int asr_shard_push(void* const* peer_base, int world, int rank, int64_t offset, int64_t pitch, const int* seg_off, int nseg,
+                   int seg_len, const int32_t* d_rows, int64_t num_rows, const uint32_t* d_mask, void* stream) {
+    return guarded([&] {
+        ASRB_REQUIRE(peer_base && seg_off, "shard_push: null argument");
+        shard_push(peer_base, world, rank, offset, pitch, seg_off, nseg, seg_len, d_rows, num_rows, d_mask, S(stream));
+    });
+}
+
 int asr_gx_overflow(void* stream, int* flag) {
     return guarded([&] {
         ASRB_REQUIRE(flag, "null argument");

@@ -23,6 +23,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <ctime>
 #include <vector>
 
 namespace asrb {
@@ -180,14 +182,17 @@ record_heads_kernel(const Key* __restrict__ key, const unsigned long long* __res
 __global__ void __launch_bounds__(256)
 balance_candidates_kernel(const Key* __restrict__ frontier, long long nf, const KeyTableView groups,
                           const Key* __restrict__ new_keys, long long nn, long long* __restrict__ cand_pos,
-                          unsigned long long cap, unsigned long long* __restrict__ count) {
+                          Key* __restrict__ cand_key, unsigned long long cap, unsigned long long* __restrict__ count) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= nf) return;
     const Key g = frontier[i];
     if (__clzll((long long)g) <= 1 || !first_sibling_is_leaf(groups, g)) return;
     if (find_key(new_keys, nn, g << 3) < 0) return;
     const unsigned long long pos = atomicAdd(count, 1ULL);
-    if (pos < cap) cand_pos[pos] = i;
+    if (pos < cap) {
+        cand_pos[pos] = i;
+        cand_key[pos] = g;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -224,6 +229,7 @@ static size_t strip_skip(const Key* d, size_t n, cudaStream_t s) {
 
 void octree_build(Octree& t, const float* d_points, const float* d_radii, int64_t n, float radius_scale,
                   int max_depth, cudaStream_t s) {
+    PhaseTimer pt(s);
     FrameDev fd;
     for (int l = 0; l <= kMaxLevel; ++l) fd.vs[l] = t.frame.vs[l];
     fd.inv_finest = t.frame.ivs[kMaxLevel];
@@ -246,6 +252,7 @@ void octree_build(Octree& t, const float* d_points, const float* d_radii, int64_
     size_t nb = unique_u64(pk.get(), (size_t)n, s);
     nb = strip_skip(pk.get(), nb, s);
     t.any = d2h_scalar(any.get(), s) != 0;
+    pt.lap("octree: point groups", (long long)nb);
 
     // 2. closure under "parent exists, with all its siblings"
     const int A = kMaxLevel - 1;
@@ -264,6 +271,7 @@ void octree_build(Octree& t, const float* d_points, const float* d_radii, int64_
     DevBuf<Key> groups(ng, s);
     if (ng) ASRB_CUDA(cudaMemcpyAsync(groups.get(), all.get(), ng * sizeof(Key), cudaMemcpyDeviceToDevice, s));
     all.release();
+    pt.lap("octree: ancestor closure", (long long)ng);
 
     // 3. 2:1 face balance to a fixed point (octree.cpp:152-206).
     // The reference sweeps the first-sibling keys SEQUENTIALLY — pass 1 in the iteration order of its hash map
@@ -298,6 +306,7 @@ void octree_build(Octree& t, const float* d_points, const float* d_radii, int64_
             cap = (size_t)produced;  // overflow: rerun the round with an exact-size buffer
         }
         ++t.balance_rounds;
+        pt.lap("octree: balance emit", (long long)produced);
         if (produced == 0) break;
         // records ordered by (group, rank): stable radix sorts, rank first
         sort_pairs_u64_u64((Key*)rec_rank.get(), (unsigned long long*)rec_key.get(), (size_t)produced, s);
@@ -310,29 +319,37 @@ void octree_build(Octree& t, const float* d_points, const float* d_radii, int64_
         ASRB_CHECK_LAUNCH();
         size_t nn = (size_t)d2h_scalar(counter.get(), s);
         sort_pairs_u64_u64(new_key.get(), new_rank.get(), nn, s);  // the heads were appended in arbitrary order
-        const size_t cand_cap = 1 << 16;
+        const size_t cand_cap = std::max<size_t>(nn, 1);  // a candidate's child group is one of the nn new groups
         DevBuf<long long> cand(cand_cap, s);
+        DevBuf<Key> cand_key(cand_cap, s);
         balance_candidates_kernel<<<grid_for(nf, 256), 256, 0, s>>>(frontier.get(), (long long)nf, table.view(),
-                                                                   new_key.get(), (long long)nn, cand.get(), cand_cap,
-                                                                   counter.get() + 1);
+                                                                   new_key.get(), (long long)nn, cand.get(),
+                                                                   cand_key.get(), cand_cap, counter.get() + 1);
         ASRB_CHECK_LAUNCH();
         const size_t nc = (size_t)d2h_scalar(counter.get() + 1, s);
+        pt.lap("octree: balance sort+cand", (long long)nc);
         if (nc > 0) {
             // sequential resolution on the host, in sweep order
             ASRB_REQUIRE(nc <= cand_cap, "octree balance: too many order-dependent keys in one pass");
-            std::vector<long long> cpos(nc);
+            std::vector<long long> cpos_u(nc);
+            std::vector<Key> ckey_u(nc);
             std::vector<Key> hk((size_t)produced);
             std::vector<unsigned long long> hr((size_t)produced);
-            ASRB_CUDA(cudaMemcpyAsync(cpos.data(), cand.get(), nc * sizeof(long long), cudaMemcpyDeviceToHost, s));
+            ASRB_CUDA(cudaMemcpyAsync(cpos_u.data(), cand.get(), nc * sizeof(long long), cudaMemcpyDeviceToHost, s));
+            ASRB_CUDA(cudaMemcpyAsync(ckey_u.data(), cand_key.get(), nc * sizeof(Key), cudaMemcpyDeviceToHost, s));
             ASRB_CUDA(cudaMemcpyAsync(hk.data(), rec_key.get(), produced * sizeof(Key), cudaMemcpyDeviceToHost, s));
             ASRB_CUDA(cudaMemcpyAsync(hr.data(), rec_rank.get(), produced * sizeof(unsigned long long),
                                       cudaMemcpyDeviceToHost, s));
             ASRB_CUDA(cudaStreamSynchronize(s));
-            std::sort(cpos.begin(), cpos.end());
+            std::vector<size_t> order(nc);
+            for (size_t c = 0; c < nc; ++c) order[c] = c;
+            std::sort(order.begin(), order.end(), [&](size_t x, size_t y) { return cpos_u[x] < cpos_u[y]; });
+            std::vector<long long> cpos(nc);
             std::vector<Key> ckey(nc);
-            for (size_t c = 0; c < nc; ++c)
-                ASRB_CUDA(cudaMemcpyAsync(&ckey[c], frontier.get() + cpos[c], sizeof(Key), cudaMemcpyDeviceToHost, s));
-            ASRB_CUDA(cudaStreamSynchronize(s));
+            for (size_t c = 0; c < nc; ++c) {
+                cpos[c] = cpos_u[order[c]];
+                ckey[c] = ckey_u[order[c]];
+            }
             std::vector<char> invalid(nc, 0);
             auto emitter_invalid = [&](unsigned long long j) {
                 auto it = std::lower_bound(cpos.begin(), cpos.end(), (long long)j);
@@ -369,6 +386,7 @@ void octree_build(Octree& t, const float* d_points, const float* d_radii, int64_
                 ASRB_CUDA(cudaStreamSynchronize(s));
             }
         }
+        pt.lap("octree: balance resolve", (long long)nn);
         if (nn == 0) break;
         // merge: the new groups are disjoint from `groups` by construction
         DevBuf<Key> merged(ng + nn, s);
@@ -382,6 +400,7 @@ void octree_build(Octree& t, const float* d_points, const float* d_radii, int64_
         frontier.alloc(nn, s);
         ASRB_CUDA(cudaMemcpyAsync(frontier.get(), new_key.get(), nn * sizeof(Key), cudaMemcpyDeviceToDevice, s));
         nf = nn;
+        pt.lap("octree: balance merge", (long long)ng);
     }
 
     // 4. nodes, leaf flags, sorted leaves
@@ -408,6 +427,7 @@ void octree_build(Octree& t, const float* d_points, const float* d_radii, int64_
                                                                        t.leaves.get());
         ASRB_CHECK_LAUNCH();
     }
+    pt.lap("octree: leaves", (long long)t.num_leaves);
 }
 
 }  // namespace asrb

@@ -2,6 +2,9 @@
 // Disabled by default (zero overhead beyond one branch); bench.py enables it to
 // measure the dominant kernel's average launch duration inside the timed region.
 #pragma once
+#include <cstdlib>
+#include <ctime>
+
 #include "common.cuh"
 
 namespace asrb {
@@ -27,6 +30,31 @@ struct ProfileScope {
             cudaEventRecord(e1, s);
             profile_push(name, e0, e1, flops);
         }
+    }
+};
+
+// ASR_DEBUG_TIMING=1: host-synchronised wall time of the phases of a build on stderr (development aid)
+struct PhaseTimer {
+    bool on;
+    cudaStream_t s;
+    double t0;
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    }
+    explicit PhaseTimer(cudaStream_t stream) : on(getenv("ASR_DEBUG_TIMING") != nullptr), s(stream), t0(0) {
+        if (on) {
+            cudaStreamSynchronize(s);
+            t0 = now();
+        }
+    }
+    void lap(const char* what, long long n = -1) {
+        if (!on) return;
+        cudaStreamSynchronize(s);
+        const double t = now();
+        fprintf(stderr, "[asr timing] %-28s %8.3f ms  (n = %lld)\n", what, t - t0, n);
+        t0 = t;
     }
 };
 

@@ -30,6 +30,7 @@
 #include <cuda.h>
 
 #include <mutex>
+#include <vector>
 
 #include "internal.h"
 #include "prims.cuh"
@@ -40,27 +41,35 @@
 namespace asrb {
 namespace gx {
 
+static int g_tma_gather = 0;  // dev knob: 1 = gather with TMA tile::gather4 instead of cp.async
+void set_tma_gather(int v) { g_tma_gather = v != 0; }
 static int g_acc_groups = 0;  // dev knob: main-accumulator groups per TMEM buffer (0 = as many as fit, <= 4)
 void set_acc_groups(int g) { g_acc_groups = g; }
 
 namespace {
 constexpr int kRowBlockShift = 15;  // rare entries are grouped by blocks of 2^15 output rows
-constexpr int kThreads = 192;       // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kProducerWarps = 4;
+constexpr int kMmaWarp = kProducerWarps;                  // warps 0-3 gather, warp 4 MMA, warps 5-12 epilogue
+constexpr int kEpilogueWarps = 8;                         // two per TMEM lane quarter, half of the columns each
+constexpr int kThreads = (kProducerWarps + 1 + kEpilogueWarps) * 32;
 constexpr uint32_t kATile = kTM * 128;  // 128 rows x 128 bytes
 
 __device__ int g_overflow_flag = 0;
 
 // ------------------------------------------------------------------------------------------ plan
 // rare entries (slot >= D) per row
+// `row_map` (may be null): the plan covers the table rows row_map[0 .. V) only (this rank's rows of a sharded
+// level); local row v = table row row_map[v]
 __global__ void __launch_bounds__(256)
 rare_count_kernel(const int64_t* __restrict__ splits, const uint8_t* __restrict__ slot, long long V, int D,
-                  int32_t* __restrict__ cnt) {
+                  const int32_t* __restrict__ row_map, int32_t* __restrict__ cnt) {
     const long long v = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3;
     const int sub = threadIdx.x & 7;
     int n = 0;
     if (v < V) {
-        const int64_t e = splits[v + 1];
-        for (int64_t j = splits[v] + sub; j < e; j += 8) n += slot[j] >= D;
+        const long long gv = row_map ? row_map[v] : v;
+        const int64_t e = splits[gv + 1];
+        for (int64_t j = splits[gv] + sub; j < e; j += 8) n += slot[j] >= D;
     }
     n += __shfl_xor_sync(0xffffffffu, n, 1);
     n += __shfl_xor_sync(0xffffffffu, n, 2);
@@ -76,19 +85,22 @@ __global__ void __launch_bounds__(256) fill_i32_kernel(int32_t* __restrict__ p, 
 // dense entries -> gather table; rare entries -> (sort key, source row) at their row-major rare position
 __global__ void __launch_bounds__(256)
 plan_fill_kernel(const int64_t* __restrict__ splits, const int32_t* __restrict__ idx, const uint8_t* __restrict__ slot,
-                 long long V, int D, const int64_t* __restrict__ rare_rs, int32_t* __restrict__ gidx,
-                 uint32_t* __restrict__ rare_key, int32_t* __restrict__ rare_src) {
+                 long long V, int D, const int32_t* __restrict__ row_map, const int64_t* __restrict__ rare_rs,
+                 int32_t* __restrict__ gidx, uint32_t* __restrict__ rare_key, int32_t* __restrict__ rare_src,
+                 int32_t* __restrict__ rare_row) {
     const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (v >= V) return;
+    const long long gv = row_map ? row_map[v] : v;
     int64_t p = rare_rs[v];
-    const int64_t e = splits[v + 1];
-    for (int64_t j = splits[v]; j < e; ++j) {
+    const int64_t e = splits[gv + 1];
+    for (int64_t j = splits[gv]; j < e; ++j) {
         const int k = slot[j];
         if (k < D) {
             gidx[((v >> 7) * D + k) * kTM + (v & 127)] = idx[j];
         } else {
             rare_key[p] = ((uint32_t)(v >> kRowBlockShift) << 8) | (uint32_t)k;
             rare_src[p] = idx[j];
+            if (rare_row) rare_row[p] = (int32_t)gv;  // pair-final form: the destination is the (table) row itself
             ++p;
         }
     }
@@ -171,23 +183,41 @@ pair_tile_fill_kernel(const int4* __restrict__ tiles, const int* __restrict__ nu
     if (r == 0) pt_slot[t] = tile.x;
 }
 
-// row of every CSR entry (kModePairFinal: the destination of a pair is its output row)
-__global__ void __launch_bounds__(256)
-entry_row_kernel(const int64_t* __restrict__ splits, long long V, int32_t* __restrict__ rows) {
-    const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (v >= V) return;
-    for (int64_t j = splits[v]; j < splits[v + 1]; ++j) rows[j] = (int32_t)v;
-}
+}  // namespace
 
+// pinned int64 slots for the plans' rare-entry counts: pooled (cudaMallocHost / cudaFreeHost synchronise the device)
+namespace {
+std::mutex g_slot_mutex;
+std::vector<int64_t*> g_slot_free;
+int64_t* slot_acquire() {
+    std::lock_guard<std::mutex> lock(g_slot_mutex);
+    if (g_slot_free.empty()) {
+        int64_t* page = nullptr;
+        ASRB_CUDA(cudaMallocHost((void**)&page, 128 * sizeof(int64_t)));  // lives as long as the library
+        for (int i = 0; i < 128; ++i) g_slot_free.push_back(page + i);
+    }
+    int64_t* p = g_slot_free.back();
+    g_slot_free.pop_back();
+    return p;
+}
+void slot_release(int64_t* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_slot_mutex);
+    g_slot_free.push_back(p);
+}
 }  // namespace
 
 Plan::~Plan() {
-    if (R_event) cudaEventDestroy(R_event);
-    if (R_host) cudaFreeHost(R_host);
+    if (R_event) {
+        if (!finished) cudaEventSynchronize(R_event);  // the async copy into the slot must have landed
+        cudaEventDestroy(R_event);
+    }
+    slot_release(R_host);
 }
 
 void plan_begin(Plan& P, const int32_t* d_idx, const uint8_t* d_slot, const int64_t* d_splits, int64_t V, int64_t V_in,
-                int64_t E, int K, int mode, cudaStream_t s) {
+                int64_t E, int K, int mode, const int32_t* d_row_map, cudaStream_t s) {
+    P.d_row_map = d_row_map;
     ASRB_REQUIRE(K >= 1 && K <= 255, "gx plan: kernel_size must be in [1, 255]");
     ASRB_REQUIRE(V < (int64_t(1) << 31) - 2 && V_in < (int64_t(1) << 31) - 2 && E < (int64_t(1) << 31),
                  "gx plan: table too large");
@@ -208,11 +238,11 @@ void plan_begin(Plan& P, const int32_t* d_idx, const uint8_t* d_slot, const int6
     ProfileScope prof("gx_plan_build", s);
     DevBuf<int32_t> cnt((size_t)std::max<int64_t>(V, 1), s);
     if (V > 0) {
-        rare_count_kernel<<<grid_for((size_t)V * 8, 256), 256, 0, s>>>(d_splits, d_slot, V, P.D, cnt.get());
+        rare_count_kernel<<<grid_for((size_t)V * 8, 256), 256, 0, s>>>(d_splits, d_slot, V, P.D, d_row_map, cnt.get());
         ASRB_CHECK_LAUNCH();
     }
     exclusive_sum_i32_to_i64(cnt.get(), P.rare_rs.get(), (size_t)V, s);
-    if (!P.R_host) ASRB_CUDA(cudaMallocHost((void**)&P.R_host, sizeof(int64_t)));
+    if (!P.R_host) P.R_host = slot_acquire();
     if (!P.R_event) ASRB_CUDA(cudaEventCreateWithFlags(&P.R_event, cudaEventDisableTiming));
     ASRB_CUDA(cudaMemcpyAsync(P.R_host, P.rare_rs.get() + V, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     ASRB_CUDA(cudaEventRecord(P.R_event, s));
@@ -226,6 +256,7 @@ void plan_finish(Plan& P, cudaStream_t s) {
     const int64_t V = P.V, R = P.R;
     const int32_t zero_row = (int32_t)P.V_in;  // the all-zero row that follows the input tensor's rows
     ProfileScope prof("gx_plan_build", s);
+    PhaseTimer pt(s);
     if (P.D > 0) {
         const size_t n = (size_t)P.T * P.D * kTM;
         P.gidx.alloc(std::max<size_t>(n, 1), s);
@@ -237,11 +268,15 @@ void plan_finish(Plan& P, cudaStream_t s) {
     DevBuf<uint32_t> key((size_t)std::max<int64_t>(R, 1), s), perm((size_t)std::max<int64_t>(R, 1), s);
     P.rare_in.alloc((size_t)std::max<int64_t>(R, 1), s);
     DevBuf<int32_t>& src = P.rare_in;
+    DevBuf<int32_t> rows;
+    if (P.mode == kModePairFinal) rows.alloc((size_t)std::max<int64_t>(R, 1), s);
     if (V > 0) {
-        plan_fill_kernel<<<grid_for((size_t)V, 256), 256, 0, s>>>(P.d_splits, P.d_idx, P.d_slot, V, P.D, P.rare_rs.get(),
-                                                                 P.gidx.get(), key.get(), src.get());
+        plan_fill_kernel<<<grid_for((size_t)V, 256), 256, 0, s>>>(P.d_splits, P.d_idx, P.d_slot, V, P.D, P.d_row_map,
+                                                                 P.rare_rs.get(), P.gidx.get(), key.get(), src.get(),
+                                                                 P.mode == kModePairFinal ? rows.get() : nullptr);
         ASRB_CHECK_LAUNCH();
     }
+    pt.lap("gx plan: fill", (long long)R);
     const int num_blocks = (int)std::max<int64_t>((V + (int64_t(1) << kRowBlockShift) - 1) >> kRowBlockShift, 1);
     const int G = num_blocks * P.K;
     P.max_pair_tiles = (int)(R / kTM) + G + 1;
@@ -255,18 +290,14 @@ void plan_finish(Plan& P, cudaStream_t s) {
         int bits = 8;
         while (bits < 31 && (int64_t(1) << (bits - 8)) < num_blocks) ++bits;
         sort_pairs_u32_u32(key.get(), perm.get(), (size_t)R, s, bits);
+        pt.lap("gx plan: sort", (long long)R);
         DevBuf<long long> g_begin((size_t)G + 1, s);
         group_begin_kernel<<<grid_for((size_t)G + 1, 256), 256, 0, s>>>(key.get(), R, P.K, G, g_begin.get());
         ASRB_CHECK_LAUNCH();
         DevBuf<int4> tiles((size_t)P.max_pair_tiles, s);
         pair_tile_list_kernel<<<1, 256, 0, s>>>(P.K, G, g_begin.get(), tiles.get(), P.pt_count.get());
         ASRB_CHECK_LAUNCH();
-        DevBuf<int32_t> rows;
-        if (P.mode == kModePairFinal) {
-            rows.alloc((size_t)R, s);  // R == E: position in the rare order == CSR position
-            entry_row_kernel<<<grid_for((size_t)V, 256), 256, 0, s>>>(P.d_splits, V, rows.get());
-            ASRB_CHECK_LAUNCH();
-        }
+        pt.lap("gx plan: tile list", (long long)G);
         pair_tile_fill_kernel<<<(unsigned)P.max_pair_tiles, kTM, 0, s>>>(
                 tiles.get(), P.pt_count.get(), perm.get(), src.get(), P.mode == kModePairFinal ? rows.get() : nullptr,
                 zero_row, P.pt_slot.get(), P.pt_gidx.get(), P.pt_out.get());
@@ -274,6 +305,7 @@ void plan_finish(Plan& P, cudaStream_t s) {
     } else {
         ASRB_CUDA(cudaMemsetAsync(P.pt_count.get(), 0, sizeof(int), s));
     }
+    pt.lap("gx plan: tile fill", (long long)P.max_pair_tiles);
     P.d_idx = nullptr;
     P.d_slot = nullptr;
     P.d_splits = nullptr;
@@ -379,8 +411,11 @@ struct KArgs {
     int num_tiles;             // stationary kind
     int D;                     // steps per stationary tile
     int V;
-    // input (coordinates into the tensor map)
+    // input: rows of x_pitch halves, hi / lo planes at columns a_hi / a_lo (also the tensor-map coordinates)
+    const __half* x;
+    int x_pitch;
     int a_hi, a_lo, chunks;
+    int tma_gather;
     // filters
     const uint8_t* wp;
     unsigned long long slot_bytes;
@@ -399,6 +434,7 @@ struct KArgs {
     const float* norm;
     int relu, ncols;
     const int64_t* rare_rs;
+    const int32_t* row_map;  // stationary kind: table row of every local row, or null
     const float* pairbuf;  // read (stationary)
     float* pair_out;       // written (pair-buffer kind)
     __half* out_h;
@@ -448,16 +484,17 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
     while ((int)ncols_alloc < nbuf * accw) ncols_alloc <<= 1;
     const int ntiles = KIND == kKindStationary ? a.num_tiles : *a.num_tiles_dev;
 
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         umma::tmem_alloc(&tmem_slot, ncols_alloc);
         if (lane == 0) {
             for (int i = 0; i < S; ++i) {
-                umma::mbar_init(&bar_full[i], 1);
+                // TMA gather: one arrive.expect_tx; cp.async gather: one arrival per producer thread + the filters' one
+                umma::mbar_init(&bar_full[i], a.tma_gather ? 1 : kProducerWarps * 32 + 1);
                 umma::mbar_init(&bar_empty[i], 1);
             }
             for (int i = 0; i < 2; ++i) {
                 umma::mbar_init(&bar_tfull[i], 1);
-                umma::mbar_init(&bar_tempty[i], 4);
+                umma::mbar_init(&bar_tempty[i], kEpilogueWarps);
             }
             umma::fence_barrier_init();
         }
@@ -468,30 +505,110 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
     const uint32_t tmem = tmem_slot;
     const int steps_per_tile = KIND == kKindStationary ? a.D : 1;
 
-    if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer (whole warp)
+    if (warp < kProducerWarps) {
+        // ------------------------------------------------------------------ gather producers
+        // Default: 16-byte cp.async (LDGSTS) straight into the swizzled K-major operand tiles.  Lane l of a warp
+        // instruction copies chunk l % 8 of row 4 i + l / 8: four whole 128-byte lines per instruction, written to
+        // ((chunk ^ row) & 7) * 16 inside the row's 128-byte slot (Swizzle<3,4,3>, what the MMA descriptor expects).
+        // Absent neighbours (the zero row) are zero-filled without a memory read (src-size 0).
+        // The TMA form (tile::gather4, one instruction per 4 rows x 128 bytes; dev option gx_tma_gather) is kept
+        // for reference: measured on B200 it sustains only ~1 instruction per ~100 cycles and SM (1.3-1.6 TB/s
+        // chip-wide whatever the shape), 4-5x below what the L2 delivers to the LSU path.
         int st = 0, ph = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int rl = lane >> 3, cj = lane & 7;
+        for (int tile = blockIdx.x; a.tma_gather && warp == 0 && tile < ntiles; tile += gridDim.x) {
             for (int sidx = 0; sidx < steps_per_tile; ++sidx) {
                 const long long step = KIND == kKindStationary ? (long long)tile * a.D + sidx : tile;
                 const int slot = KIND == kKindStationary ? sidx : a.tile_slot[tile];
-                const int4 r = *reinterpret_cast<const int4*>(a.gidx + step * kTM + lane * 4);
                 const uint8_t* wsrc = a.wp + (size_t)slot * a.slot_bytes;
+                {
+                    const int4 r = *reinterpret_cast<const int4*>(a.gidx + step * kTM + lane * 4);
+                    for (int c = 0; c < a.chunks; ++c) {
+                        umma::mbar_wait(&bar_empty[st], ph ^ 1);
+                        const uint32_t stage = sbase + (uint32_t)st * a.stage_bytes;
+                        const uint32_t full = umma::smem_u32(&bar_full[st]);
+                        if (lane == 0) umma::mbar_arrive_expect_tx(&bar_full[st], a.tx_bytes);
+                        __syncwarp();
+                        tma_gather4(stage + lane * 512, &tmap, a.a_hi + c * 64, r.x, r.y, r.z, r.w, full);
+                        if (!C32) tma_gather4(stage + kATile + lane * 512, &tmap, a.a_lo + c * 64, r.x, r.y, r.z, r.w, full);
+                        if (lane == 0) {
+                            const uint32_t bdst = stage + (C32 ? 1u : 2u) * kATile;
+                            asm volatile(
+                                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(bdst),
+                                    "l"(wsrc + (size_t)c * a.chunk_bytes), "r"(a.chunk_bytes), "r"(full)
+                                    : "memory");
+                        }
+                        if (++st == S) {
+                            st = 0;
+                            ph ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+        if (!a.tma_gather) {
+            // (tile, step) pairs of this CTA as one sequence, the gather rows of step q + 1 loaded while step q is
+            // being issued (the index loads are dependent global loads: without the prefetch they cost a full
+            // memory latency per step on the critical path of all four producer warps)
+            const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+            const long long nq = (long long)my_tiles * steps_per_tile;
+            auto step_of = [&](long long q, int& slot) -> long long {
+                const int tile = (int)blockIdx.x + (int)(q / steps_per_tile) * (int)gridDim.x;
+                const int sidx = (int)(q % steps_per_tile);
+                if (KIND == kKindStationary) {
+                    slot = sidx;
+                    return (long long)tile * a.D + sidx;
+                }
+                slot = a.tile_slot[tile];
+                return tile;
+            };
+            int g_next[8], slot_next = 0;
+            if (nq > 0) {
+                const long long step = step_of(0, slot_next);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g_next[i] = a.gidx[step * kTM + warp * 32 + 4 * i + rl];
+            }
+            for (long long q = 0; q < nq; ++q) {
+                int g[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g[i] = g_next[i];
+                const int slot = slot_next;
+                if (q + 1 < nq) {
+                    const long long step = step_of(q + 1, slot_next);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) g_next[i] = a.gidx[step * kTM + warp * 32 + 4 * i + rl];
+                }
+                const uint8_t* wsrc = a.wp + (size_t)slot * a.slot_bytes;
+                // the 8 rows this lane copies from: rows warp * 32 + 4 i + lane / 8
+                const __half* src[8];
+                uint32_t dst[8], nbytes[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = warp * 32 + 4 * i + rl;
+                    src[i] = a.x + (size_t)g[i] * a.x_pitch + cj * 8;
+                    nbytes[i] = g[i] == a.zero_row ? 0u : 16u;
+                    dst[i] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((cj ^ r) & 7) << 4));
+                }
                 for (int c = 0; c < a.chunks; ++c) {
                     umma::mbar_wait(&bar_empty[st], ph ^ 1);
                     const uint32_t stage = sbase + (uint32_t)st * a.stage_bytes;
-                    const uint32_t full = umma::smem_u32(&bar_full[st]);
-                    if (lane == 0) umma::mbar_arrive_expect_tx(&bar_full[st], a.tx_bytes);
-                    __syncwarp();
-                    tma_gather4(stage + lane * 512, &tmap, a.a_hi + c * 64, r.x, r.y, r.z, r.w, full);
-                    if (!C32) tma_gather4(stage + kATile + lane * 512, &tmap, a.a_lo + c * 64, r.x, r.y, r.z, r.w, full);
-                    if (lane == 0) {
+                    if (warp == 0 && lane == 0) {
                         const uint32_t bdst = stage + (C32 ? 1u : 2u) * kATile;
+                        umma::mbar_arrive_expect_tx(&bar_full[st], a.chunk_bytes);
                         asm volatile(
                                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(bdst),
-                                "l"(wsrc + (size_t)c * a.chunk_bytes), "r"(a.chunk_bytes), "r"(full)
+                                "l"(wsrc + (size_t)c * a.chunk_bytes), "r"(a.chunk_bytes), "r"(umma::smem_u32(&bar_full[st]))
                                 : "memory");
                     }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        umma::cp_async16_cg(stage + dst[i], src[i] + a.a_hi + c * 64, nbytes[i]);
+                    if (!C32) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            umma::cp_async16_cg(stage + kATile + dst[i], src[i] + a.a_lo + c * 64, nbytes[i]);
+                    }
+                    umma::cp_async_arrive_noinc(&bar_full[st]);
                     if (++st == S) {
                         st = 0;
                         ph ^= 1;
@@ -499,7 +616,7 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         // ------------------------------------------------------------------ MMA issuer (one thread)
         if (lane == 0) {
             const uint32_t idN = idesc_f16(N), id2N = idesc_f16(2 * N);
@@ -515,6 +632,9 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                 for (int sidx = 0; sidx < steps_per_tile; ++sidx) {
                     for (int c = 0; c < a.chunks; ++c, ++sc) {
                         umma::mbar_wait(&bar_full[st], ph);
+                        // the cp.async writes (generic proxy, acquired through the barrier) -> visible to the MMA's
+                        // operand reads (async proxy); this thread has no loads of its own in flight, so it is cheap
+                        umma::fence_proxy_async();
                         umma::tc_fence_after();
                         const uint32_t stage = sbase + (uint32_t)st * a.stage_bytes;
                         const int g = a.by_slot ? sidx : (sc % G);
@@ -568,9 +688,18 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
         }
         __syncwarp();
     } else {
-        // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
-        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        // ------------------------------------------------------------------ epilogue
+        // 8 warps: warp e reads TMEM lane quarter e % 4 (thread = output row / pair) and handles half e / 4 of the
+        // columns (<= 64).  The contribution of the row's rare entries does not depend on this tile's MMAs, so it is
+        // summed from the pair buffer BEFORE the wait on the accumulator (all 16-byte loads of a pair row in flight
+        // at once) and overlaps the main loop; afterwards the accumulator groups are added, the epilogue applied and
+        // the row written.
+        const int e = warp - (kMmaWarp + 1);
+        const int q = warp & 3;  // TMEM lane quarter this warp may access (warps 5..12 -> 1,2,3,0,1,2,3,0)
         const int L = q * 32 + lane;
+        const int half = e >> 2;
+        const int cph = ((N / 16 + 1) / 2) * 16;  // columns of half 0 (multiple of 16)
+        const int c0 = half ? cph : 0, c1 = half ? N : cph;
         int overflow = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -580,7 +709,7 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
             if (KIND == kKindStationary) {
                 const long long v = (long long)tile * kTM + L;
                 if (v < a.V) {
-                    row = v;
+                    row = a.row_map ? a.row_map[v] : v;
                     if (a.rare_rs) {
                         r0 = a.rare_rs[v];
                         r1 = a.rare_rs[v + 1];
@@ -604,10 +733,34 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                     }
                 }
             }
+            // rare entries of this row, columns [c0, c1): <= 64 floats in registers
+            float racc[64];
+#pragma unroll
+            for (int j = 0; j < 64; ++j) racc[j] = 0.f;
+            if (KIND == kKindStationary) {
+                for (long long p = r0; p < r1; ++p) {
+                    const float4* src = reinterpret_cast<const float4*>(a.pairbuf + (size_t)p * N + c0);
+                    const float w = a.imp ? a.imp[a.rare_in[p]] : 1.f;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (c0 + 4 * j < c1) {
+                            const float4 t = __ldg(src + j);
+                            racc[4 * j] = fmaf(t.x, w, racc[4 * j]);
+                            racc[4 * j + 1] = fmaf(t.y, w, racc[4 * j + 1]);
+                            racc[4 * j + 2] = fmaf(t.z, w, racc[4 * j + 2]);
+                            racc[4 * j + 3] = fmaf(t.w, w, racc[4 * j + 3]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
             umma::mbar_wait(&bar_tfull[buf], (it / nbuf) & 1);
             umma::tc_fence_after();
             const uint32_t t_acc = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * accw);
-            for (int n0 = 0; n0 < N; n0 += 16) {
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {
+                const int n0 = c0 + 16 * cb;
+                if (n0 >= c1) break;  // warp-uniform
                 float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = 0.f;
@@ -623,7 +776,7 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] *= a.wscale;
+                for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], a.wscale, 0.f);
                 if (row < 0 || n0 >= a.ncols) continue;
                 if (KIND == kKindPairBuf) {
                     float4* dst = reinterpret_cast<float4*>(a.pair_out + (size_t)row * N + n0);
@@ -631,20 +784,8 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                     for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     continue;
                 }
-                if (KIND == kKindStationary) {
-                    for (long long p = r0; p < r1; ++p) {
-                        const float4* src = reinterpret_cast<const float4*>(a.pairbuf + (size_t)p * N + n0);
-                        const float w = a.imp ? a.imp[a.rare_in[p]] : 1.f;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 t = __ldg(src + j);
-                            v[4 * j] = fmaf(t.x, w, v[4 * j]);
-                            v[4 * j + 1] = fmaf(t.y, w, v[4 * j + 1]);
-                            v[4 * j + 2] = fmaf(t.z, w, v[4 * j + 2]);
-                            v[4 * j + 3] = fmaf(t.w, w, v[4 * j + 3]);
-                        }
-                    }
-                }
+                for (int j = 0; j < 16; ++j) v[j] += racc[16 * cb + j];
                 const int nvalid = min(16, a.ncols - n0);  // multiple of 8
                 if (KIND != kKindPairBuf && a.norm && nrm != 0.f) {
 #pragma unroll
@@ -685,7 +826,7 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
     }
     umma::tc_fence_before();
     __syncthreads();
-    if (warp == 1) umma::tmem_dealloc(tmem, ncols_alloc);
+    if (warp == kMmaWarp) umma::tmem_dealloc(tmem, ncols_alloc);
 }
 
 // ---------------------------------------------------------------- tensor map
@@ -751,7 +892,8 @@ void conv(const Plan& P, const ConvArgs& c, cudaStream_t s) {
     const int Cin = c.x.C;
     const bool c32 = Cin == 32;
     ASRB_REQUIRE(c32 || (Cin >= 64 && Cin % 64 == 0), "gx conv: in_channels must be 32 or a multiple of 64");
-    ASRB_REQUIRE(c.ncols % 8 == 0 && c.ncols >= 8 && c.ncols <= 256, "gx conv: output columns must be a multiple of 8, <= 256");
+    ASRB_REQUIRE(c.ncols % 8 == 0 && c.ncols >= 8 && c.ncols <= 128,
+                 "gx conv: output columns must be a multiple of 8, <= 128 per call (wider banks run as column groups)");
     ASRB_REQUIRE(c.x.rows == P.V_in + 1, "gx conv: the input view must hold the plan's input rows + the zero row");
     ASRB_REQUIRE(!c32 || (c.x.hi % 64 == 0 && c.x.lo == c.x.hi + 32), "gx conv: a 32-channel input must be a plain [hi | lo] row");
     ASRB_REQUIRE((c.out.p != nullptr) != (c.out_f32 != nullptr), "gx conv: exactly one of the h2 / fp32 outputs");
@@ -759,6 +901,9 @@ void conv(const Plan& P, const ConvArgs& c, cudaStream_t s) {
     const int N = padded_n(c.ncols);
     KArgs k{};
     k.V = (int)P.V;
+    k.x = c.x.p;
+    k.x_pitch = c.x.pitch;
+    k.tma_gather = g_tma_gather;
     k.a_hi = c.x.hi;
     k.a_lo = c.x.lo;
     k.chunks = c32 ? 1 : Cin / 64;
@@ -832,6 +977,7 @@ void conv(const Plan& P, const ConvArgs& c, cudaStream_t s) {
         o.num_tiles = (int)P.T;
         o.D = P.D;
         o.rare_rs = has_rare ? P.rare_rs.get() : nullptr;
+        o.row_map = P.d_row_map;
         o.pairbuf = c.pairbuf;
         if (c.imp) {  // one accumulator group per dense slot, weighted in the epilogue
             ASRB_REQUIRE(P.D <= 8 && 2 * N * P.D <= 512, "gx conv: importance variant: too many columns");

@@ -47,6 +47,9 @@ struct Plan {
     const int32_t* d_idx = nullptr;
     const uint8_t* d_slot = nullptr;
     const int64_t* d_splits = nullptr;
+    // the plan covers the table rows d_row_map[0 .. V) only (null: all rows, local row = table row); outputs,
+    // normalisers and residuals stay indexed by table row.  The caller keeps the array alive with the plan.
+    const int32_t* d_row_map = nullptr;
     bool finished = false;
     ~Plan();
 };
@@ -54,7 +57,7 @@ struct Plan {
 // Two-phase build so that several tables share ONE host synchronisation: begin() queues the counting
 // kernels and an async copy of the rare-entry count; finish() waits for it and builds the tile lists.
 void plan_begin(Plan& P, const int32_t* d_idx, const uint8_t* d_slot, const int64_t* d_splits, int64_t V, int64_t V_in,
-                int64_t E, int K, int mode, cudaStream_t s);
+                int64_t E, int K, int mode, const int32_t* d_row_map, cudaStream_t s);
 void plan_finish(Plan& P, cudaStream_t s);
 
 // Packed filter bank for the tensor-core kernel: per slot and 64-channel chunk the fp16 hi / lo parts
@@ -82,6 +85,7 @@ struct ConvArgs {
 };
 size_t pairbuf_floats(const Plan& P, int ncols);
 void set_acc_groups(int g);
+void set_tma_gather(int v);
 void conv(const Plan& P, const ConvArgs& a, cudaStream_t s);
 
 // format conversion and the elementwise helpers of the split-half format

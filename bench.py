@@ -261,7 +261,7 @@ def run_gpu(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from asr_b200 import _lib, clouds, model, ops, pipeline, shard
+    from asr_b200 import _lib, clouds, model, ops, pipeline, shard, shard_gx
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -280,21 +280,29 @@ def run_gpu(args):
     # exchange before every sharded convolution (asr_b200/shard.py) -> strong scaling
     cloud = make_cloud(args, args.points, on_gpu=True)
     net = model.seeded_weights(model.UNet(args.levels), seed=0).cuda()
-    if world > 1:
-        # rows owned by contiguous index range (default) or by spatial region (ASR_SHARD=spatial: 19x
-        # less halo traffic, but its torch-level bookkeeping still costs more than it saves)
+    ctx = None
+    if world > 1 and args.backend == "gx":
+        # rows of every grid level owned by Z-curve region, gx plans per rank, halo rows pushed peer to peer through a
+        # symmetric-memory arena (asr_b200/shard_gx.py)
+        arena = shard_gx.Arena(int(float(os.environ.get("ASR_SHARD_ARENA_GB", "40")) * (1 << 30)), dist.group.WORLD)
+        ctx = shard_gx.ShardContext(arena)
+    elif world > 1:
+        # round-1 path: rows owned by contiguous index range, NCCL point-to-point halo exchange per convolution
         net.K = (shard.SpatialShardedOps if os.environ.get("ASR_SHARD") == "spatial" else shard.ShardedOps)(ops)
     host = {k: torch.from_numpy(cloud[k]).pin_memory() for k in ("points", "normals", "radii")}
     devt = {k: v.cuda() for k, v in host.items()}
     bb = (cloud["bb_min"], cloud["bb_max"])
 
-    def step_device():
-        return pipeline.reconstruct_vertices(net, devt["points"], devt["normals"], devt["radii"], bb[0], bb[1])
+    def step_device(timer=None):
+        if ctx is not None:
+            return shard_gx.reconstruct_vertices(net, ctx, devt["points"], devt["normals"], devt["radii"], bb[0], bb[1],
+                                                 timer=timer)
+        return pipeline.reconstruct_vertices(net, devt["points"], devt["normals"], devt["radii"], bb[0], bb[1], timer=timer)
 
     def step_host():
         # the public host-buffer entry point: pinned H2D of the cloud, the path, D2H of vertices + values
         res = pipeline.reconstruct_vertices_host(net, host["points"], host["normals"], host["radii"], bb[0], bb[1],
-                                                 pinned_out=True)
+                                                 pinned_out=True, shard_ctx=ctx)
         return None, res["vertices"], res["values"]
 
     def barrier():
@@ -304,8 +312,25 @@ def run_gpu(args):
 
     # one accounted step (untimed) for sizes and the byte model
     ops.ACCOUNT = []
-    out = pipeline.reconstruct_vertices(net, devt["points"], devt["normals"], devt["radii"], bb[0], bb[1])
+    out = step_device()
     convs, ops.ACCOUNT = ops.ACCOUNT, None
+    parity = None
+    if world > 1:
+        # the sharded result against the single-GPU path on the same cloud (rank 0 runs it once, untimed)
+        barrier()
+        if rank == 0:
+            saved_k = net.K
+            net.K = ops
+            one = pipeline.reconstruct_vertices(net, devt["points"], devt["normals"], devt["radii"], bb[0], bb[1])
+            net.K = saved_k
+            parity = {"values_max_abs": float((one["values"] - out["values"]).abs().max()),
+                      "vertex_dual_equal": bool(one["vertex_dual"].shape == out["vertex_dual"].shape and
+                                                torch.equal(one["vertex_dual"], out["vertex_dual"])),
+                      "vertices_equal": bool(one["vertices"].shape == out["vertices"].shape and
+                                             torch.equal(one["vertices"], out["vertices"])),
+                      "vertices": int(one["vertices"].shape[0])}
+            del one
+        barrier()
     d = out["input_dict"]
     sizes = {"N": args.points,
              "V": [int(d["neighbors_row_splits%d" % i].shape[0] - 1) for i in range(args.levels)],
@@ -320,7 +345,7 @@ def run_gpu(args):
     # last warm-up step: host-synchronised per stage (its sum slightly exceeds ms_per_step)
     tm = pipeline.StageTimer(enabled=not args.profile_run)
     if not args.profile_run:
-        pipeline.reconstruct_vertices(net, devt["points"], devt["normals"], devt["radii"], bb[0], bb[1], timer=tm)
+        step_device(timer=tm)
     stage_ms = {k: round(v, 3) for k, v in tm.ms.items()}
 
     # ---- device-resident timing (value) with the kernel profiler on
@@ -331,6 +356,7 @@ def run_gpu(args):
     _lib.profile_reset()
     _lib.profile_enable(True)
     launches0 = _lib.kernel_launches()
+    mem0 = torch.cuda.memory_stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -339,6 +365,14 @@ def run_gpu(args):
     barrier()
     ms_dev = e0.elapsed_time(e1)
     launches = (_lib.kernel_launches() - launches0) // max(args.steps, 1)
+    mem1 = torch.cuda.memory_stats()
+    pool = _lib.pool_stats()
+    memory = {"torch_cudamalloc_calls_in_timed_region": mem1.get("num_device_alloc", 0) - mem0.get("num_device_alloc", 0),
+              "torch_alloc_retries_in_timed_region": mem1.get("num_alloc_retries", 0) - mem0.get("num_alloc_retries", 0),
+              "torch_reserved_gb": round(mem1.get("reserved_bytes.all.current", 0) / 1e9, 2),
+              "torch_peak_allocated_gb": round(mem1.get("allocated_bytes.all.peak", 0) / 1e9, 2),
+              "library_pool_reserved_gb": round(pool[0] / 1e9, 2), "library_pool_used_gb": round(pool[1] / 1e9, 2),
+              "library_pool_keeps_freed_memory": pool[2] > (1 << 60)}
     _lib.profile_enable(False)
     prof = _lib.profile_read()
     clocks = sampler.stop()
@@ -416,23 +450,30 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong" if world > 1 else "weak",
+            "scaling": "strong",
             "vs_baseline": None, "dtype": {"gx": "f32 (fp16 hi/lo split operands, fp32 accumulation on tcgen05 for the sparse convs)",
                                           "tensor": "f32 (3xTF32 on tcgen05 for the sparse convs)"}.get(ops.SPARSE_CONV_BACKEND, "f32"),
             "data": "synthetic",
-            "config": {"workload": workload_name(args), "sparse_conv_backend": ops.SPARSE_CONV_BACKEND, "parallelism": ("%d gpus: geometry replicated, search/conv/decode sharded by %s, "
-                                       "peer-to-peer halo-row exchange before each sharded conv (%d exchanges, %.3f GB "
-                                       "received per rank and step)"
-                                       % (world, "spatial region (Z-curve cut)" if isinstance(net.K, shard.SpatialShardedOps)
-                                          else "output-voxel index ranges", net.K.collectives // max(total_steps, 1),
-                                          net.K.bytes_gathered / max(total_steps, 1) / 1e9)) if world > 1 else "1 gpu",
+            "config": {"workload": workload_name(args), "sparse_conv_backend": ops.SPARSE_CONV_BACKEND, "parallelism": (
+                ("%d gpus: geometry replicated; search / aggregation / every convolution / decoder on the rows a rank owns "
+                 "(Z-curve regions of equal level-0 voxel count, every grid level); halo rows pushed with peer stores into "
+                 "a symmetric-memory arena + device-side barrier after each convolution (%d exchanges per step); two NCCL "
+                 "all-reduces (pair counts, first V0 pair importances)" % (world, ctx.exchanges // max(total_steps, 1)))
+                if ctx is not None else
+                ("%d gpus: geometry replicated, search/conv/decode sharded by %s, peer-to-peer halo-row exchange before each "
+                 "sharded conv (%d exchanges, %.3f GB received per rank and step)"
+                 % (world, "spatial region (Z-curve cut)" if isinstance(net.K, shard.SpatialShardedOps)
+                    else "output-voxel index ranges", net.K.collectives // max(total_steps, 1),
+                    net.K.bytes_gathered / max(total_steps, 1) / 1e9))) if world > 1 else "1 gpu",
                        "l2_policy": "inputs and every intermediate tensor larger than the 126 MB L2",
                        "sizes": sizes},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_step_e2e},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "path_roofline": path,
+            "gpu_launches": int(launches), "clocks": clocks, "memory": memory, "roofline": roofline, "path_roofline": path,
             "stage_ms_synchronised_untimed_step": stage_ms, "kernel_ms": kernels,
         }
+        if parity is not None:
+            line["parity_vs_1gpu"] = parity
         if world == 1 and not args.no_cpu_baseline:
             v, dt, cores, sample, _, kind = cpu_pipeline_points_per_s(args, args.cpu_points or 200_000)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}

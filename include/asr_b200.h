@@ -43,6 +43,8 @@ int64_t asr_kernel_launches(void);
  * that carry no importance through the output-stationary tensor-core kernel (sparse_conv_os.cu). */
 int asr_set_option(const char* name, int value);
 
+/* bytes reserved / in use / release threshold of the stream-ordered memory pool the library allocates from */
+int asr_pool_stats(int64_t* reserved_bytes, int64_t* used_bytes, int64_t* release_threshold);
 /* Per-kernel device timing (CUDA events on the launching stream) for bench.py's
  * roofline figures: enable, run, then read (name, total ms, launches, algorithmic
  * flops) per instrumented kernel.  Reading synchronises the recorded events. */
@@ -175,9 +177,12 @@ int asr_invert_neighbors_list(int64_t num_points, const int32_t* d_inp_neighbors
  * _plan_begin queues the counting kernels, _plan_finish (one host synchronisation, shared by all plans begun
  * before it) completes the plan and returns the number of rare entries (pair-buffer rows). */
 typedef struct asr_gx_plan asr_gx_plan;
+/* d_row_map (may be NULL): the plan covers only the table rows d_row_map[0 .. num_out) (one rank's rows of a
+ * sharded grid level, ascending); outputs / normalisers / residuals stay indexed by table row.  The array must
+ * outlive the plan. */
 int asr_gx_plan_begin(const int32_t* d_neighbors_index, const uint8_t* d_neighbors_kernel_index,
                       const int64_t* d_neighbors_row_splits, int64_t num_out, int64_t num_in, int64_t num_entries,
-                      int kernel_size, int mode, void* stream, asr_gx_plan** out);
+                      int kernel_size, int mode, const int32_t* d_row_map, void* stream, asr_gx_plan** out);
 int asr_gx_plan_finish(asr_gx_plan* plan, void* stream, int64_t* num_rare);
 void asr_gx_plan_destroy(asr_gx_plan* plan);
 /* filters [K, Cin, Cout] fp32 -> fp16 hi/lo of W * 2^scale_exp for output columns [col0, col0 + ncols) in the
@@ -203,6 +208,23 @@ int asr_gx_conv(const asr_gx_plan* plan, const void* d_x, int in_channels, int x
                 int out_lo, float* d_out_f32, int out_f32_pitch, float* d_pairbuf, void* stream);
 /* 1 if a conversion to the split-half format saturated (|x| > 65504) since the last call; synchronises */
 int asr_gx_overflow(void* stream, int* flag);
+
+/* ---------------------------------------------------------------- multi-GPU sharding helpers
+ * The reference is single-process; these serve the sharded form of the path (one process per GPU, geometry
+ * replicated, every grid level's rows owned by Z-curve region, csrc/shard.cu).  All asynchronous on `stream`.
+ * _positions: Z-curve position (depth 21) of every location code; _owner: owner rank of every voxel = number of
+ * thresholds <= its position (thresholds = region boundaries, ascending, world - 1 of them);
+ * _need_mask: ORs into d_mask[row of the input level] the ranks (bit r) whose output rows read that row through the
+ * neighbour table, for rows owned by `rank`; _push: copies the listed (owned) rows — the bytes [seg_off[i],
+ * seg_off[i] + seg_len) of each row — into the same buffer on every rank flagged in d_mask (NULL: all ranks) through
+ * the peer-mapped base pointers of a symmetric allocation (buffer = base + offset on every rank). */
+int asr_shard_positions(const uint64_t* d_keys, int64_t num_voxels, uint64_t* d_pos, void* stream);
+int asr_shard_owner(const uint64_t* d_keys, int64_t num_voxels, const uint64_t* d_thresholds, int num_thresholds,
+                    uint8_t* d_owner, void* stream);
+int asr_shard_need_mask(const int64_t* d_row_splits, const int32_t* d_index, int64_t num_out, const uint8_t* d_owner_out,
+                        const uint8_t* d_owner_in, int rank, uint32_t* d_mask, void* stream);
+int asr_shard_push(void* const* peer_base, int world, int rank, int64_t offset, int64_t pitch, const int* seg_off, int nseg,
+                   int seg_len, const int32_t* d_rows, int64_t num_rows, const uint32_t* d_mask, void* stream);
 
 /* ---------------------------------------------------------------- decoder MLP
  * replaces UNet5.decode / decode_with_gradient, net_definitions_torch.py:655-686.

@@ -56,17 +56,17 @@ def test_within_grid_conv_matches_oracle(cin, cout):
     cpu = {k: v.cpu() for k, v in g.items()}
     ref = ops_cpu.sparse_conv(W, xs.to_f32().cpu(), torch.empty(0), cpu["neighbors_index"], cpu["neighbors_kernel_index"],
                               torch.empty(0), cpu["neighbors_row_splits"], False, dtype=torch.float64)
-    y = gx.conv(plan, xs, gx.Filters(W.cuda(), bias=b.cuda()), relu=True).to_f32()
+    y = gx.conv(plan, xs, gx.filter_bank(W.cuda(), b.cuda()), relu=True).to_f32()
     want = torch.relu(ref + b.double())
     assert (y.cpu().double() - want).abs().max() <= TOL
     # fp32 output, no activation, a residual
     r = torch.randn((V, cout), generator=gen)
     rs = gx.from_f32(r.cuda())
     out = torch.empty((V, cout), dtype=torch.float32, device="cuda")
-    gx.conv(plan, xs, gx.Filters(W.cuda(), bias=b.cuda()), relu=False, res=rs, out_f32=out)
+    gx.conv(plan, xs, gx.filter_bank(W.cuda(), b.cuda()), relu=False, res=rs, out_f32=out)
     assert (out.cpu().double() - (ref + b.double() + rs.to_f32().cpu().double())).abs().max() <= TOL
     # bit-reproducible: no atomics anywhere on this path; as column groups (what the model does for wide banks)
-    y2 = gx.conv(plan, xs, gx.Filters(W.cuda(), bias=b.cuda()), relu=True).to_f32()
+    y2 = gx.conv(plan, xs, gx.filter_bank(W.cuda(), b.cuda()), relu=True).to_f32()
     assert torch.equal(y, y2)
     y3 = gx.conv(plan, xs, gx.filter_bank(W.cuda(), b.cuda(), max_cols=max(16, cout // 2)), relu=True).to_f32()
     assert (y3.cpu().double() - want).abs().max() <= TOL
@@ -129,7 +129,7 @@ def test_transition_convs_match_oracle(cin, cout):
     inv = ops.invert_neighbors_list(V1, ui, us, uk)
     plan = gx.Plan(inv.neighbors_index, inv.neighbors_attributes, inv.neighbors_row_splits, V0, 9, gx.MODE_STATIONARY)
     x = gx.from_f32(torch.randn((V0, cin), generator=gen).cuda())
-    y = gx.conv(plan, x, gx.Filters(W.cuda(), bias=b.cuda()), relu=True).to_f32()
+    y = gx.conv(plan, x, gx.filter_bank(W.cuda(), b.cuda()), relu=True).to_f32()
     ref = ops_cpu.sparse_conv(W, x.to_f32().cpu(), torch.empty(0), inv.neighbors_index.cpu(), inv.neighbors_attributes.cpu(),
                               torch.empty(0), inv.neighbors_row_splits.cpu(), False, dtype=torch.float64)
     assert y.shape == (V1, cout)
@@ -140,7 +140,7 @@ def test_transition_convs_match_oracle(cin, cout):
     xc = gx.from_f32(torch.randn((V1, cout), generator=gen).cuda())
     wide = gx.H2.empty(V0, cin + 64, "cuda")
     wide.buf[:V0].fill_(7.0)
-    gx.conv(plan_up, xc, gx.Filters(W2.cuda()), relu=True, out=wide.slice(0, cin))
+    gx.conv(plan_up, xc, gx.filter_bank(W2.cuda()), relu=True, out=wide.slice(0, cin))
     ref = ops_cpu.sparse_conv(W2, xc.to_f32().cpu(), torch.empty(0), ui.cpu(), uk.cpu(), torch.empty(0), us.cpu(), False,
                               dtype=torch.float64)
     assert (wide.slice(0, cin).to_f32().cpu().double() - torch.relu(ref)).abs().max() <= TOL

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( timeout 900 python -m pytest tests/test_gpu_gx.py -q -x 2>&1 | tail -15 ) > gpurun_out/s5_gx.log 2>&1
+( ASR_DEBUG_TIMING=1 timeout 600 python bench.py --steps 1 --warmup 3 --no-cpu-baseline ) > gpurun_out/s5_bench_timing.json 2> gpurun_out/s5_bench_timing.err
+( timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/s5_bench_gx.json ) 2> gpurun_out/s5_bench_gx.err
+( timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --radii analytic > gpurun_out/s5_bench_gx_analytic.json ) 2> gpurun_out/s5_bench_gx_analytic.err
+echo done
