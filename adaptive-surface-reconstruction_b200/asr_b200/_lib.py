@@ -23,7 +23,7 @@ SIGNATURES = {
     "asr_last_error": (C.c_char_p, []),
     "asr_kernel_launches": (_i64, []),
     "asr_set_option": (_i32, [C.c_char_p, _i32]),
-    "asr_pool_stats": (_i32, [_pi64, _pi64, _pi64]),
+    "asr_pool_stats": (_i32, [_pi64, _pi64, _pi64, _pi64]),
     "asr_profile_enable": (None, [_i32]),
     "asr_profile_reset": (None, []),
     "asr_profile_count": (_i32, []),
@@ -40,6 +40,8 @@ SIGNATURES = {
     "asr_grids_get": (_i32, [_vp, _i32] + [_vp] * 10),
     "asr_duals_count": (_i32, [_vp, _pi64, _vp]),
     "asr_duals_fill": (_i32, [_vp, _vp, _vp]),
+    "asr_duals_begin": (_i32, [_vp, _vp]),
+    "asr_duals_check": (_i32, [_vp]),
     "asr_radius_search_create": (_i32, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _pp, _pi64]),
     "asr_radius_search_fill": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "asr_radius_search_destroy": (None, [_vp]),
@@ -57,7 +59,7 @@ SIGNATURES = {
     "asr_gx_plan_destroy": (None, [_vp]),
     "asr_gx_packed_filters_bytes": (_i64, [_i32, _i32, _i32]),
     "asr_gx_pack_filters": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
-    "asr_gx_from_f32": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "asr_gx_from_f32": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp]),
     "asr_gx_to_f32": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "asr_gx_scale_rows": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _vp]),
     "asr_gx_conv": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32,
@@ -89,10 +91,10 @@ _lib = None
 
 
 def pool_stats():
-    """(reserved, used, release threshold) bytes of the library's stream-ordered memory pool"""
-    a, b, c = _i64(0), _i64(0), _i64(0)
-    check(lib().asr_pool_stats(C.byref(a), C.byref(b), C.byref(c)))
-    return a.value, b.value, c.value
+    """(reserved, used, release threshold, high-water mark in use) bytes of the library's stream-ordered memory pool"""
+    a, b, c, d = _i64(0), _i64(0), _i64(0), _i64(0)
+    check(lib().asr_pool_stats(C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+    return a.value, b.value, c.value, d.value
 
 
 def lib():

@@ -58,11 +58,13 @@ class H2:
         return out
 
 
-def from_f32(x, row_scale=None, out=None):
+def from_f32(x, row_scale=None, out=None, rows=None):
+    """fp32 [n, C] -> split-half.  rows (int32, with `out` given): input row i goes to row rows[i] of `out`, no other
+    row of `out` is touched."""
     x = ops._cuda(x, torch.float32, "x")
     V, C_ = x.shape
     out = out or H2.empty(V, C_, x.device)
-    check(lib().asr_gx_from_f32(_ptr(x), V, C_, C_, _ptr(row_scale), *out.args(), _stream()))
+    check(lib().asr_gx_from_f32(_ptr(x), V, C_, C_, _ptr(row_scale), _ptr(rows), out.V, *out.args(), _stream()))
     return out
 
 

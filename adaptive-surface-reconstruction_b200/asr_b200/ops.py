@@ -145,11 +145,24 @@ class Octree:
 
     def dual_vertex_indices(self):
         """[num_duals, 8] int64 leaf indices (reference CreateDualVertexIndices, grid.cpp:450)."""
+        out = self.dual_vertex_indices_finish()
+        check(lib().asr_duals_check(self._h))
+        return out
+
+    # asynchronous form for the pipeline: begin (counting pass queued, no host synchronisation) ... finish (waits for
+    # the count, queues the fill) ... dual_check() before the result is trusted.  Both may run on a side stream.
+    def dual_vertex_indices_begin(self):
+        check(lib().asr_duals_begin(self._h, _stream()))
+
+    def dual_vertex_indices_finish(self):
         n = _i64(0)
         check(lib().asr_duals_count(self._h, C.byref(n), _stream()))
         out = torch.empty((n.value, 8), dtype=torch.int64, device=self.device)
         check(lib().asr_duals_fill(self._h, _ptr(out), _stream()))
         return out
+
+    def dual_check(self):
+        check(lib().asr_duals_check(self._h))
 
 
 # ------------------------------------------------------------------------------------ aggregation search

@@ -35,8 +35,51 @@ class StageTimer:
             self._t = now
 
 
+_SIDE_STREAM = None
+
+
+def side_stream():
+    """second CUDA stream of the pipeline: the dual-cell passes (needed only by the contouring at the very end) run
+    there, next to the grid / search / network stages — all of them latency-bound kernels that leave most of the GPU idle"""
+    global _SIDE_STREAM
+    if _SIDE_STREAM is None:
+        _SIDE_STREAM = torch.cuda.Stream()
+    return _SIDE_STREAM
+
+
+class AsyncDuals:
+    """Dual vertex indices computed on the side stream; `get()` joins the streams and returns the tensor."""
+
+    def __init__(self, tree, enabled=True):
+        self.tree, self.out = tree, None
+        self.enabled = enabled and hasattr(tree, "dual_vertex_indices_begin")
+        if self.enabled:
+            self.main = torch.cuda.current_stream()
+            self.side = side_stream()
+            self.side.wait_stream(self.main)  # the octree was built on the main stream
+            with torch.cuda.stream(self.side):
+                tree.dual_vertex_indices_begin()
+
+    def fill(self):
+        """after some main-stream work was queued: wait for the count (done long ago), queue the fill"""
+        if self.enabled and self.out is None:
+            with torch.cuda.stream(self.side):
+                self.out = self.tree.dual_vertex_indices_finish()
+
+    def get(self):
+        if not self.enabled:
+            if self.out is None:
+                self.out = self.tree.dual_vertex_indices()
+            return self.out
+        self.fill()
+        self.main.wait_stream(self.side)
+        self.out.record_stream(self.main)
+        self.tree.dual_check()
+        return self.out
+
+
 def build_input_dict(points, normals, radii, bb_min, bb_max, levels=5, radius_scale=1.0, max_depth=21, timer=None,
-                     K=ops, normals_ready=None):
+                     K=ops, normals_ready=None, async_duals=False):
     """Grid building + aggregation search (asr.cpp:143-312).  Returns
     (input_dict, dual_vertex_indices, octree).  K = kernel namespace (ops or
     shard.ShardedOps: there the aggregation arrays cover this rank's voxels).
@@ -45,10 +88,15 @@ def build_input_dict(points, normals, radii, bb_min, bb_max, levels=5, radius_sc
     timer.start()
     tree = K.Octree(points, radii, bb_min, bb_max, radius_scale, 0, max_depth)
     timer.lap("octree")
-    duals = tree.dual_vertex_indices()
+    if async_duals and not timer.enabled:
+        duals = AsyncDuals(tree)  # runs beside the next stages; the caller joins with duals.get()
+    else:
+        duals = tree.dual_vertex_indices()
     timer.lap("duals")
     grids = tree.grids(levels, True)
     timer.lap("grids")
+    if isinstance(duals, AsyncDuals):
+        duals.fill()
     ones = torch.ones((points.shape[0], 1), dtype=torch.float32, device=points.device)
     if normals_ready is not None:
         torch.cuda.current_stream().wait_event(normals_ready)
@@ -97,8 +145,10 @@ def reconstruct_vertices(model, points, normals, radii, bb_min=None, bb_max=None
         bb_max = points.max(0).values.cpu().numpy()
     K = getattr(model, "K", ops)
     d, duals, tree = build_input_dict(points, normals, radii, bb_min, bb_max, levels, radius_scale, max_depth, timer, K,
-                                      normals_ready)
+                                      normals_ready, async_duals=K is ops)
     values = run_network(model, d, timer)
+    if isinstance(duals, AsyncDuals):
+        duals = duals.get()
     timer.start()
     tris = None
     if triangles:

@@ -118,10 +118,16 @@ class ShardContext(gx.LocalContext):
             inv = ops.invert_neighbors_list(V[l + 1], ui, us, uk)
             self.inv.append(inv)
             self._need(inv.neighbors_row_splits, inv.neighbors_index, l + 1, l)  # down table: rows on l + 1 read l
+        self.border = []
         for l in range(levels):
+            rows = torch.nonzero(self.owner[l] == self.rank).reshape(-1).to(torch.int32)
+            self.rows.append(rows)
             if V[l] < self.min_rows:
                 self.need[l] = None  # small level: every owned row goes to every rank
-            self.rows.append(torch.nonzero(self.owner[l] == self.rank).reshape(-1).to(torch.int32))
+                self.border.append(rows)
+            else:
+                # the owned rows somebody else reads (the region border): the only rows a push has to look at
+                self.border.append(rows[self.need[l][rows.long()] != 0].contiguous())
         self.V = V
         self.levels = levels
 
@@ -156,12 +162,12 @@ class ShardContext(gx.LocalContext):
         input_dict["_asr_gx_shard_plans"] = P
         return P
 
-    def push_rows(self, tensor, level, seg_off, seg_len):
+    def push_rows(self, tensor, level, seg_off, seg_len, all_rows=None):
         """copies this rank's rows of `tensor` (a view into the arena, row-major 2-D) that other ranks read into
         their copies; then a cross-rank barrier on the stream."""
         if self.world > 1:
-            rows = self.rows[level]
-            mask = self.need[level]
+            rows = self.border[level] if all_rows is None else all_rows
+            mask = self.need[level] if all_rows is None else None
             segs = (C.c_int * 2)(*(list(seg_off) + [0])[:2])
             pitch = tensor.stride(0) * tensor.element_size()
             check(lib().asr_shard_push(self.arena.peers, self.world, self.rank, self.arena.offset_of(tensor), pitch, segs,
@@ -186,10 +192,13 @@ def reconstruct_vertices(net, ctx, points, normals, radii, bb_min, bb_max, level
     timer.start()
     tree = ops.Octree(points, radii, bb_min, bb_max, radius_scale, 0, max_depth)
     timer.lap("octree")
-    duals = tree.dual_vertex_indices()
+    duals = pipeline.AsyncDuals(tree, enabled=not timer.enabled)  # side stream, joined before the contouring
+    if timer.enabled:
+        duals.get()
     timer.lap("duals")
     grids = tree.grids(levels, True)
     timer.lap("grids")
+    duals.fill()
     d = {"points": points}
     for i, g in enumerate(grids):
         for k, v in g.items():
@@ -234,12 +243,14 @@ def reconstruct_vertices(net, ctx, points, normals, radii, bb_min, bb_max, level
             first[s_own[sel][seg] + within] = imp_pairs[lo[seg] + within]
     if world > 1:
         dist.all_reduce(first, group=ctx.arena.group)
-    # ---- features into the symmetric split-half buffer (owned rows), halo pushed
-    full = torch.empty((V0, feats_own.shape[1]), dtype=torch.float32, device=points.device)
-    full[own0_l] = feats_own
+    # ---- features into the symmetric split-half buffer: ONLY the owned rows are written (the other ranks push their
+    # rows into this buffer at their own pace), then the halo is pushed
     x0 = ctx.empty(V0, feats_own.shape[1], points.device)
-    gx.from_f32(full, out=x0)
+    gx.from_f32(feats_own, out=x0, rows=own0)
     ctx.done(x0, 0)
+    d["aggregation_neighbors_index"], d["aggregation_neighbors_dist"], d["aggregation_row_splits"] = idx, dist2, rs
+    d["aggregation_scale_compat"] = compat
+    d["aggregation_pairs_total"] = int(start[-1] + counts[-1])
     timer.lap("aggregate")
     code = ctx.arena.alloc((V0, 32), torch.float32)
     gx.unet(net, (None, first), d, ctx=ctx, x0=x0, code=code)
@@ -251,6 +262,7 @@ def reconstruct_vertices(net, ctx, points, normals, radii, bb_min, bb_max, level
     if world > 1:
         _broadcast_values(ctx, values)  # every rank contours the whole field
     timer.lap("decode")
+    duals = duals.get()
     verts, vdual = ops.contour_vertices(values, duals, d["voxel_centers0"], contouring_value_threshold)
     timer.lap("contour")
     return {"vertices": verts, "vertex_dual": vdual, "values": values, "dual_vertex_indices": duals, "input_dict": d,
@@ -264,9 +276,5 @@ def _broadcast_values(ctx, values):
     wide = ctx.arena.alloc((V0, 4), torch.float32)
     own = ctx.rows[0].long()
     wide[own, :2] = values[own]
-    saved, ctx.need[0] = ctx.need[0], None
-    try:
-        ctx.push_rows(wide, 0, (0,), 16)
-    finally:
-        ctx.need[0] = saved
+    ctx.push_rows(wide, 0, (0,), 16, all_rows=ctx.rows[0])
     values.copy_(wide[:, :2])

@@ -105,23 +105,19 @@ int64_t asr_kernel_launches(void) { return (int64_t)g_kernel_launches.load(); }
 int asr_set_option(const char* name, int value) {
     return guarded([&] {
         ASRB_REQUIRE(name != nullptr, "option name is null");
-        if (std::string(name) == "sparse_conv_output_stationary") sparse_conv_os_enable(value != 0);
-        else if (std::string(name) == "sparse_conv_persistent") sparse_conv_pm_enable(value != 0);
-        else if (std::string(name) == "pm_debug") {
-            sparse_conv_pm_debug(value);
-            sparse_conv_os_debug(value);
-        }
-        else if (std::string(name) == "conv_row_block_shift") sparse_conv_row_block_shift(value);
+        if (std::string(name) == "conv_row_block_shift") sparse_conv_row_block_shift(value);
         else if (std::string(name) == "tc_ntile") sparse_conv_tc_ntile(value);
         else if (std::string(name) == "gx_acc_groups") gx::set_acc_groups(value);
         else if (std::string(name) == "gx_tma_gather") gx::set_tma_gather(value);
+        else if (std::string(name) == "gx_l1_gather") gx::set_l1_gather(value);
+        else if (std::string(name) == "gx_max_stages") gx::set_max_stages(value);
         else if (std::string(name) == "tc_stages") sparse_conv_tc_tune(value, 0);
         else if (std::string(name) == "tc_row_groups") sparse_conv_tc_tune(0, value);
         else throw Error(kInvalidArgument, std::string("unknown option: ") + name);
     });
 }
 
-int asr_pool_stats(int64_t* reserved_bytes, int64_t* used_bytes, int64_t* release_threshold) {
+int asr_pool_stats(int64_t* reserved_bytes, int64_t* used_bytes, int64_t* release_threshold, int64_t* used_high_bytes) {
     return guarded([&] {
         int dev = 0;
         ASRB_CUDA(cudaGetDevice(&dev));
@@ -135,6 +131,10 @@ int asr_pool_stats(int64_t* reserved_bytes, int64_t* used_bytes, int64_t* releas
         if (used_bytes) {
             ASRB_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &v));
             *used_bytes = (int64_t)v;
+        }
+        if (used_high_bytes) {
+            ASRB_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &v));
+            *used_high_bytes = (int64_t)v;
         }
         if (release_threshold) {
             ASRB_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &v));
@@ -243,10 +243,22 @@ int asr_duals_count(asr_octree* tree, int64_t* num_duals, void* stream) {
         *num_duals = tree->t.num_duals;
     });
 }
+int asr_duals_begin(asr_octree* tree, void* stream) {
+    return guarded([&] {
+        ASRB_REQUIRE(tree, "tree is null");
+        duals_begin(tree->t, S(stream));
+    });
+}
 int asr_duals_fill(asr_octree* tree, int64_t* d_out, void* stream) {
     return guarded([&] {
         ASRB_REQUIRE(tree, "tree is null");
         duals_fill(tree->t, d_out, S(stream));
+    });
+}
+int asr_duals_check(asr_octree* tree) {
+    return guarded([&] {
+        ASRB_REQUIRE(tree, "tree is null");
+        duals_check(tree->t);
     });
 }
 
@@ -396,11 +408,12 @@ static gx::H2View h2view(const void* p, int64_t num_rows, int C, int pitch, int 
     v.lo = lo;
     return v;
 }
-int asr_gx_from_f32(const float* d_x, int64_t num_rows, int channels, int ldx, const float* d_row_scale, void* d_out,
-                    int out_pitch, int out_hi, int out_lo, void* stream) {
+int asr_gx_from_f32(const float* d_x, int64_t num_rows, int channels, int ldx, const float* d_row_scale,
+                    const int32_t* d_rows, int64_t out_rows, void* d_out, int out_pitch, int out_hi, int out_lo,
+                    void* stream) {
     return guarded([&] {
-        gx::from_f32(d_x, num_rows, channels, ldx, d_row_scale, h2view(d_out, num_rows, channels, out_pitch, out_hi, out_lo),
-                     S(stream));
+        gx::from_f32(d_x, num_rows, channels, ldx, d_row_scale, d_rows,
+                     h2view(d_out, d_rows ? out_rows : num_rows, channels, out_pitch, out_hi, out_lo), S(stream));
     });
 }
 int asr_gx_to_f32(const void* d_x, int64_t num_rows, int channels, int pitch, int hi, int lo, float* d_out, int ldo,

@@ -355,8 +355,21 @@ dual_fill_kernel(const Key* __restrict__ leaves, long long V, const KeyTableView
     }
 }
 
-void duals_count(Octree& t, cudaStream_t s) {
-    if (t.num_duals >= 0) return;
+Octree::~Octree() {
+    if (dual_count_event) {
+        cudaEventSynchronize(dual_count_event);
+        cudaEventDestroy(dual_count_event);
+    }
+    if (dual_err_event) {
+        cudaEventSynchronize(dual_err_event);
+        cudaEventDestroy(dual_err_event);
+    }
+    pinned_slot_release(dual_count_host);
+    pinned_slot_release(dual_err_host);
+}
+
+void duals_begin(Octree& t, cudaStream_t s) {
+    if (t.num_duals >= 0 || t.dual_begun) return;
     const long long V = t.num_leaves;
     t.dual_mask.alloc((size_t)V, s);
     t.dual_offset.alloc((size_t)V + 1, s);
@@ -369,22 +382,49 @@ void duals_count(Octree& t, cudaStream_t s) {
         ASRB_CHECK_LAUNCH();
     }
     exclusive_sum_u8_to_i64(count.get(), t.dual_offset.get(), (size_t)V, s);
-    t.num_duals = d2h_scalar(t.dual_offset.get() + V, s);
+    if (!t.dual_count_host) t.dual_count_host = pinned_slot_acquire();
+    if (!t.dual_count_event) ASRB_CUDA(cudaEventCreateWithFlags(&t.dual_count_event, cudaEventDisableTiming));
+    ASRB_CUDA(cudaMemcpyAsync(t.dual_count_host, t.dual_offset.get() + V, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    ASRB_CUDA(cudaEventRecord(t.dual_count_event, s));
+    t.dual_begun = true;
 }
 
+void duals_count(Octree& t, cudaStream_t s) {
+    if (t.num_duals >= 0) return;
+    duals_begin(t, s);
+    ASRB_CUDA(cudaEventSynchronize(t.dual_count_event));
+    t.num_duals = *t.dual_count_host;
+}
+
+// the fill is queued without a host synchronisation; its error flag (the reference's "found node is not a leaf",
+// grid.cpp:436-440) is read by duals_check
 void duals_fill(Octree& t, int64_t* d_out, cudaStream_t s) {
     duals_count(t, s);
     const long long V = t.num_leaves;
     if (!V || !t.num_duals) return;
-    DevBuf<int> err(1, s);
-    ASRB_CUDA(cudaMemsetAsync(err.get(), 0, sizeof(int), s));
-    ProfileScope prof("dual_fill", s);
-    dual_fill_kernel<<<grid_for((size_t)V * 8, 256), 256, 0, s>>>(t.leaves.get(), V, t.group_table.view(),
-                                                                  t.root_separate, t.node_leaf.get(),
-                                                                  t.node_rank.get(), t.dual_mask.get(),
-                                                                  t.dual_offset.get(), d_out, err.get());
-    ASRB_CHECK_LAUNCH();
-    if (d2h_scalar(err.get(), s)) throw Error(kRuntimeError, "found node is not a leaf");
+    t.dual_err.alloc(1, s);
+    ASRB_CUDA(cudaMemsetAsync(t.dual_err.get(), 0, sizeof(int), s));
+    {
+        ProfileScope prof("dual_fill", s);
+        dual_fill_kernel<<<grid_for((size_t)V * 8, 256), 256, 0, s>>>(t.leaves.get(), V, t.group_table.view(),
+                                                                      t.root_separate, t.node_leaf.get(),
+                                                                      t.node_rank.get(), t.dual_mask.get(),
+                                                                      t.dual_offset.get(), d_out, t.dual_err.get());
+        ASRB_CHECK_LAUNCH();
+    }
+    if (!t.dual_err_host) t.dual_err_host = pinned_slot_acquire();
+    if (!t.dual_err_event) ASRB_CUDA(cudaEventCreateWithFlags(&t.dual_err_event, cudaEventDisableTiming));
+    *t.dual_err_host = 0;
+    ASRB_CUDA(cudaMemcpyAsync(t.dual_err_host, t.dual_err.get(), sizeof(int), cudaMemcpyDeviceToHost, s));
+    ASRB_CUDA(cudaEventRecord(t.dual_err_event, s));
+    t.dual_err_pending = true;
+}
+
+void duals_check(Octree& t) {
+    if (!t.dual_err_pending) return;
+    ASRB_CUDA(cudaEventSynchronize(t.dual_err_event));
+    t.dual_err_pending = false;
+    if ((int)(*t.dual_err_host & 0xffffffff)) throw Error(kRuntimeError, "found node is not a leaf");
 }
 
 }  // namespace asrb

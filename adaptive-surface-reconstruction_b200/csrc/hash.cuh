@@ -42,8 +42,11 @@ struct KeyTable {
     DevBuf<HashEntry> entries;
     uint32_t mask = 0;
     KeyTableView view() const { return KeyTableView{entries.get(), mask}; }
-    // keys must be unique and != kNoKey; value of keys[i] is i
-    void build(const Key* d_keys, size_t n, cudaStream_t s);
+    // keys must be unique and != kNoKey; value of keys[i] is i; `reserve`: capacity for that many keys in total
+    void build(const Key* d_keys, size_t n, cudaStream_t s, size_t reserve = 0);
+    // adds keys (value base + i) to a table whose capacity allows it (load factor stays <= 0.5 up to `reserve`)
+    void insert(const Key* d_keys, size_t n, size_t base, cudaStream_t s);
+    size_t capacity() const { return (size_t)mask + 1; }
 };
 
 }  // namespace asrb

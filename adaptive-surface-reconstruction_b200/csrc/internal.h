@@ -51,6 +51,13 @@ struct Octree {
     int64_t num_duals = -1;
     DevBuf<uint8_t> dual_mask;     // [num_leaves] bit i = corner i emits a dual
     DevBuf<int64_t> dual_offset;   // [num_leaves+1]
+    // asynchronous form (duals_begin / duals_fill): count and error flag travel to pinned slots behind events
+    int64_t* dual_count_host = nullptr;
+    int64_t* dual_err_host = nullptr;
+    cudaEvent_t dual_count_event = nullptr, dual_err_event = nullptr;
+    DevBuf<int> dual_err;
+    bool dual_begun = false, dual_err_pending = false;
+    ~Octree();
 };
 
 // octree.cu
@@ -58,7 +65,9 @@ void octree_build(Octree& t, const float* d_points, const float* d_radii, int64_
                   int max_depth, cudaStream_t s);
 // grids.cu
 void grids_build(Octree& t, int num_levels, bool all_info, cudaStream_t s);
-void duals_count(Octree& t, cudaStream_t s);
+void duals_begin(Octree& t, cudaStream_t s);   // queues the counting pass, no host synchronisation
+void duals_count(Octree& t, cudaStream_t s);   // waits for it (or runs it)
+void duals_check(Octree& t);                    // waits for duals_fill's error flag; throws like the reference
 void duals_fill(Octree& t, int64_t* d_out, cudaStream_t s);
 
 }  // namespace asrb

@@ -287,9 +287,14 @@ void octree_build(Octree& t, const float* d_points, const float* d_radii, int64_
     if (ng) ASRB_CUDA(cudaMemcpyAsync(frontier.get(), groups.get(), ng * sizeof(Key), cudaMemcpyDeviceToDevice, s));
     DevBuf<unsigned long long> counter(2, s);
     t.balance_rounds = 0;
+    // membership table of the node set: built once with room to grow (balancing adds a few percent), the groups a
+    // pass creates are inserted; `groups` is appended to and sorted once at the end
     KeyTable table;
+    size_t table_room = ng + ng / 4 + 4096;
+    if (nf > 0) table.build(groups.get(), ng, s, table_room);
+    size_t groups_cap = ng;
+    const size_t ng_before_balance = ng;
     while (nf > 0) {
-        table.build(groups.get(), ng, s);
         size_t cap = std::max<size_t>(nf * 4, 1 << 16);
         DevBuf<Key> rec_key;
         DevBuf<unsigned long long> rec_rank;
@@ -388,12 +393,21 @@ void octree_build(Octree& t, const float* d_points, const float* d_radii, int64_
         }
         pt.lap("octree: balance resolve", (long long)nn);
         if (nn == 0) break;
-        // merge: the new groups are disjoint from `groups` by construction
-        DevBuf<Key> merged(ng + nn, s);
-        ASRB_CUDA(cudaMemcpyAsync(merged.get(), groups.get(), ng * sizeof(Key), cudaMemcpyDeviceToDevice, s));
-        ASRB_CUDA(cudaMemcpyAsync(merged.get() + ng, new_key.get(), nn * sizeof(Key), cudaMemcpyDeviceToDevice, s));
-        sort_keys_u64(merged.get(), ng + nn, s);
-        groups = std::move(merged);
+        // the new groups (disjoint from `groups` by construction) are appended and added to the membership table
+        if (ng + nn > groups_cap) {
+            const size_t new_cap = std::max(ng + nn, groups_cap + groups_cap / 8 + 4096);
+            DevBuf<Key> grown(new_cap, s);
+            ASRB_CUDA(cudaMemcpyAsync(grown.get(), groups.get(), ng * sizeof(Key), cudaMemcpyDeviceToDevice, s));
+            groups = std::move(grown);
+            groups_cap = new_cap;
+        }
+        ASRB_CUDA(cudaMemcpyAsync(groups.get() + ng, new_key.get(), nn * sizeof(Key), cudaMemcpyDeviceToDevice, s));
+        if (ng + nn > table_room) {  // rare: the table would exceed its load factor -> rebuild with more room
+            table_room = (ng + nn) + (ng + nn) / 4 + 4096;
+            table.build(groups.get(), ng + nn, s, table_room);
+        } else {
+            table.insert(new_key.get(), nn, ng, s);
+        }
         ng += nn;
         // next pass: the created groups in creation order
         sort_pairs_u64_u64((Key*)new_rank.get(), (unsigned long long*)new_key.get(), nn, s);
@@ -402,6 +416,7 @@ void octree_build(Octree& t, const float* d_points, const float* d_radii, int64_
         nf = nn;
         pt.lap("octree: balance merge", (long long)ng);
     }
+    if (ng > ng_before_balance) sort_keys_u64(groups.get(), ng, s);  // ascending node order for the leaf pass
 
     // 4. nodes, leaf flags, sorted leaves
     t.num_groups = (int64_t)ng;

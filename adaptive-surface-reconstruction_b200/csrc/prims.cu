@@ -2,19 +2,68 @@
 
 #include "prims.cuh"
 
+#include <cstdlib>
+#include <mutex>
+#include <vector>
+
 namespace asrb {
 
-static bool g_pool_ready = false;
+// The library's scratch and handle-owned storage come from the device's default stream-ordered pool.  Two settings,
+// once per device: (i) freed blocks stay in the pool (release threshold = max), (ii) the pool is grown ONCE to
+// ASR_POOL_PREALLOC_GB (default 16) in one piece.  Without (ii) the pool holds just the high-water mark of a pass
+// (~4 GB for 10 M points); the GB-sized transient buffers of the search and of the conv plans then regularly fail
+// to find a contiguous free range and the driver re-maps physical memory inside the pool — measured in round 2 as
+// sporadic host stalls of 30-600 ms inside cudaMallocAsync.
+static std::mutex g_pool_mutex;
+static bool g_pool_ready[64] = {};
 void ensure_pool_configured() {
-    if (g_pool_ready) return;
     int dev = 0;
     cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return;
+    if (g_pool_ready[dev]) return;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (g_pool_ready[dev]) return;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
         uint64_t thr = ~uint64_t(0);  // keep freed blocks cached in the pool
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        double gb = 16.0;
+        if (const char* e = getenv("ASR_POOL_PREALLOC_GB")) gb = atof(e);
+        size_t free_b = 0, total_b = 0;
+        if (gb > 0 && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            size_t want = (size_t)(gb * (double)(1ull << 30));
+            want = std::min(want, free_b / 4);  // never more than a quarter of what is free
+            void* p = nullptr;
+            if (want > (64u << 20) && cudaMallocAsync(&p, want, (cudaStream_t)0) == cudaSuccess) {
+                cudaFreeAsync(p, (cudaStream_t)0);
+                cudaStreamSynchronize((cudaStream_t)0);
+            } else {
+                cudaGetLastError();
+            }
+        }
     }
-    g_pool_ready = true;
+    g_pool_ready[dev] = true;
+}
+
+// pinned int64 slots for small asynchronous device-to-host results (cudaMallocHost / cudaFreeHost synchronise the
+// device, so the slots are pooled and never freed)
+static std::mutex g_slot_mutex;
+static std::vector<int64_t*> g_slot_free;
+int64_t* pinned_slot_acquire() {
+    std::lock_guard<std::mutex> lock(g_slot_mutex);
+    if (g_slot_free.empty()) {
+        int64_t* page = nullptr;
+        ASRB_CUDA(cudaMallocHost((void**)&page, 128 * sizeof(int64_t)));
+        for (int i = 0; i < 128; ++i) g_slot_free.push_back(page + i);
+    }
+    int64_t* p = g_slot_free.back();
+    g_slot_free.pop_back();
+    return p;
+}
+void pinned_slot_release(int64_t* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_slot_mutex);
+    g_slot_free.push_back(p);
 }
 
 template <class K>

@@ -19,4 +19,8 @@ size_t unique_u64(Key* d_keys, size_t n, cudaStream_t s);
 void exclusive_sum_i32_to_i64(const int32_t* d_in, int64_t* d_out, size_t n, cudaStream_t s);
 void exclusive_sum_u8_to_i64(const uint8_t* d_in, int64_t* d_out, size_t n, cudaStream_t s);
 
+// pooled pinned host slots for asynchronous scalar read-backs
+int64_t* pinned_slot_acquire();
+void pinned_slot_release(int64_t* p);
+
 }  // namespace asrb

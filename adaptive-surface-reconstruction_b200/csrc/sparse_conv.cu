@@ -191,7 +191,7 @@ void flag_slot_release(int* p) {
 }
 
 void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, const int64_t* d_splits, int64_t V_out,
-                     int64_t E, int K, cudaStream_t s, bool with_output_stationary) {
+                     int64_t E, int K, cudaStream_t s) {
     ASRB_REQUIRE(K >= 1 && K <= 256, "sparse_conv: kernel_size must be in [1, 256]");
     ASRB_REQUIRE(E < (int64_t(1) << 31), "sparse_conv: too many neighbour entries");
     ASRB_REQUIRE(V_out < (int64_t(1) << 31), "sparse_conv: too many output rows");
@@ -261,9 +261,6 @@ void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, c
         ASRB_CUDA(cudaEventRecord(P.flag_event, s));
         P.flag_pending = true;
     }
-
-    if (with_output_stationary && sparse_conv_os_enabled() && K == 55 && V_out > 0)
-        os_plan_build(P, d_idx, d_slot, d_splits, V_out, K, s);
 }
 
 // ------------------------------------------------------------------ tile kernel
@@ -525,36 +522,17 @@ void sparse_conv_forward(const ConvPlan& P, const float* x, const float* w, cons
                          const int64_t* splits, const float* bias, int relu, float* out, cudaStream_t s) {
     ASRB_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0, "sparse_conv: channel counts must be multiples of 4");
     if (P.V_out == 0) return;
-    if (wp && !imp_in && !imp_entry && !normalize && sparse_conv_os_supported(P, Cin, Cout)) {
-        // common slots output-stationary (writes every row once); the sparse slots, if any, are
-        // reduced into that by the pair-major kernel before the bias / ReLU pass
-        const bool has_rare = P.rare && P.rare->E > 0;
-        sparse_conv_os(P, x, wp, Cin, Cout, has_rare ? nullptr : bias, has_rare ? 0 : relu, out, s);
-        if (has_rare) {
-            sparse_conv_tc_tiles(*P.rare, x, wp, Cin, Cout, nullptr, nullptr, Cout, out, s);
-            if (bias || relu) {
-                ProfileScope prof("sparse_conv_epilogue", s);
-                conv_epilogue_kernel<<<grid_for((size_t)P.V_out * (Cout / 4), 256), 256, 0, s>>>(
-                        out, P.V_out, Cout, 0, 0, nullptr, splits, bias, relu);
-                ASRB_CHECK_LAUNCH();
-            }
-        }
-        return;
-    }
     if (P.flag_pending) {
         ASRB_CUDA(cudaEventSynchronize(P.flag_event));
         P.tiles0 = *P.flag_host ? 0 : P.tiles0_if_flag;
         P.flag_pending = false;
     }
-    const bool store_first = wp && P.E > 0 && P.tiles0 > 0 && sparse_conv_tc_row_groups() == 1 &&
-                             !sparse_conv_pm_supported(P, Cin, Cout);
+    const bool store_first = wp && P.E > 0 && P.tiles0 > 0 && sparse_conv_tc_row_groups() == 1;
     if (!store_first) {
         ProfileScope prof("sparse_conv_zero", s);
         ASRB_CUDA(cudaMemsetAsync(out, 0, (size_t)P.V_out * Cout * sizeof(float), s));
     }
-    if (P.E > 0 && wp && sparse_conv_pm_supported(P, Cin, Cout)) {
-        sparse_conv_pm_tiles(P, x, wp, Cin, Cout, imp_in, imp_entry, imp_col, out, s);
-    } else if (P.E > 0 && wp) {
+    if (P.E > 0 && wp) {
         sparse_conv_tc_tiles(P, x, wp, Cin, Cout, imp_in, imp_entry, imp_col, out, s, store_first);
     } else if (P.E > 0) {
         TileArgs a;

@@ -34,14 +34,6 @@ struct ConvPlan {
     int max_tiles2 = 0;           // same for 256-pair tiles (tensor-core kernel, two 128-row MMA groups)
     DevBuf<Int4Pod> tiles2;
     DevBuf<int> num_tiles2;
-    // output-stationary form (sparse_conv_os.cu): per super-tile of 256 output rows the slots
-    // that occur ("steps") and per step the gather index of every row (-1 = absent)
-    bool os_ok = false;
-    int64_t os_steps = 0, os_tiles = 0, os_pairs = 0;  // os_pairs = entries of the output-stationary slots
-    DevBuf<int64_t> os_off;   // [os_tiles + 1]
-    DevBuf<int32_t> os_meta;  // [os_steps] slot | row-tile flags << 8
-    DevBuf<int32_t> os_idx;   // [os_steps][256]
-    std::unique_ptr<ConvPlan> rare;  // entries of the slots that are not accumulated output-stationary
 };
 
 int* flag_slot_acquire();
@@ -55,9 +47,7 @@ inline ConvPlan::~ConvPlan() {
 }
 
 void conv_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, const int64_t* d_splits, int64_t V_out,
-                     int64_t E, int K, cudaStream_t s, bool with_output_stationary = true);
-void os_plan_build(ConvPlan& P, const int32_t* d_idx, const uint8_t* d_slot, const int64_t* d_splits, int64_t V_out,
-                   int K, cudaStream_t s);
+                     int64_t E, int K, cudaStream_t s);
 
 // out must hold V_out*Cout floats.  imp_in (per input row, gathered through the
 // index) and/or imp_entry (per CSR entry) weight channels >= imp_col;
@@ -75,25 +65,10 @@ void pack_conv_filters(const float* W, int K, int Cin, int Cout, float* out, cud
 void sparse_conv_tc_tiles(const ConvPlan& P, const float* x, const float* wp, int Cin, int Cout, const float* imp_in,
                           const float* imp_entry, int imp_col, float* out, cudaStream_t s, bool store_first = false);
 
-// persistent pair-major tensor-core kernel (sparse_conv_pm.cu): filter part resident in shared
-// memory, TMEM double buffering, bulk-reduction epilogue
-bool sparse_conv_pm_supported(const ConvPlan& P, int Cin, int Cout);
-void sparse_conv_pm_enable(bool on);
-void sparse_conv_pm_debug(int on);
-void sparse_conv_pm_tiles(const ConvPlan& P, const float* x, const float* wp, int Cin, int Cout, const float* imp_in,
-                          const float* imp_entry, int imp_col, float* out, cudaStream_t s);
-
-// output-stationary persistent tensor-core path; see sparse_conv_os.cu
 void sparse_conv_tc_tune(int stages, int mt);
 void sparse_conv_row_block_shift(int v);
 void sparse_conv_tc_ntile(int n);
 int sparse_conv_tc_row_groups();
-void sparse_conv_os_enable(bool on);
-void sparse_conv_os_debug(int on);
-bool sparse_conv_os_enabled();
-bool sparse_conv_os_supported(const ConvPlan& P, int Cin, int Cout);
-void sparse_conv_os(const ConvPlan& P, const float* x, const float* wp, int Cin, int Cout, const float* bias, int relu,
-                    float* out, cudaStream_t s);
 
 void row_importance(const float* imp, const int32_t* idx, const int64_t* splits, int64_t V, float* out,
                     cudaStream_t s);

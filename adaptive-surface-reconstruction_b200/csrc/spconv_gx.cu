@@ -43,6 +43,10 @@ namespace gx {
 
 static int g_tma_gather = 0;  // dev knob: 1 = gather with TMA tile::gather4 instead of cp.async
 void set_tma_gather(int v) { g_tma_gather = v != 0; }
+static int g_l1_gather = 0;   // dev knob: gather with cp.async.ca (L1-allocating) — pair with fewer stages
+static int g_max_stages = 0;  // dev knob: cap on the pipeline stages (leaves the rest of the 228 KB to L1)
+void set_l1_gather(int v) { g_l1_gather = v != 0; }
+void set_max_stages(int v) { g_max_stages = v; }
 static int g_acc_groups = 0;  // dev knob: main-accumulator groups per TMEM buffer (0 = as many as fit, <= 4)
 void set_acc_groups(int g) { g_acc_groups = g; }
 
@@ -185,34 +189,12 @@ pair_tile_fill_kernel(const int4* __restrict__ tiles, const int* __restrict__ nu
 
 }  // namespace
 
-// pinned int64 slots for the plans' rare-entry counts: pooled (cudaMallocHost / cudaFreeHost synchronise the device)
-namespace {
-std::mutex g_slot_mutex;
-std::vector<int64_t*> g_slot_free;
-int64_t* slot_acquire() {
-    std::lock_guard<std::mutex> lock(g_slot_mutex);
-    if (g_slot_free.empty()) {
-        int64_t* page = nullptr;
-        ASRB_CUDA(cudaMallocHost((void**)&page, 128 * sizeof(int64_t)));  // lives as long as the library
-        for (int i = 0; i < 128; ++i) g_slot_free.push_back(page + i);
-    }
-    int64_t* p = g_slot_free.back();
-    g_slot_free.pop_back();
-    return p;
-}
-void slot_release(int64_t* p) {
-    if (!p) return;
-    std::lock_guard<std::mutex> lock(g_slot_mutex);
-    g_slot_free.push_back(p);
-}
-}  // namespace
-
 Plan::~Plan() {
     if (R_event) {
         if (!finished) cudaEventSynchronize(R_event);  // the async copy into the slot must have landed
         cudaEventDestroy(R_event);
     }
-    slot_release(R_host);
+    pinned_slot_release(R_host);
 }
 
 void plan_begin(Plan& P, const int32_t* d_idx, const uint8_t* d_slot, const int64_t* d_splits, int64_t V, int64_t V_in,
@@ -242,7 +224,7 @@ void plan_begin(Plan& P, const int32_t* d_idx, const uint8_t* d_slot, const int6
         ASRB_CHECK_LAUNCH();
     }
     exclusive_sum_i32_to_i64(cnt.get(), P.rare_rs.get(), (size_t)V, s);
-    if (!P.R_host) P.R_host = slot_acquire();
+    if (!P.R_host) P.R_host = pinned_slot_acquire();
     if (!P.R_event) ASRB_CUDA(cudaEventCreateWithFlags(&P.R_event, cudaEventDisableTiming));
     ASRB_CUDA(cudaMemcpyAsync(P.R_host, P.rare_rs.get() + V, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     ASRB_CUDA(cudaEventRecord(P.R_event, s));
@@ -415,7 +397,7 @@ struct KArgs {
     const __half* x;
     int x_pitch;
     int a_hi, a_lo, chunks;
-    int tma_gather;
+    int tma_gather, l1_gather;
     // filters
     const uint8_t* wp;
     unsigned long long slot_bytes;
@@ -600,13 +582,24 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                                 "l"(wsrc + (size_t)c * a.chunk_bytes), "r"(a.chunk_bytes), "r"(umma::smem_u32(&bar_full[st]))
                                 : "memory");
                     }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        umma::cp_async16_cg(stage + dst[i], src[i] + a.a_hi + c * 64, nbytes[i]);
-                    if (!C32) {
+                    if (a.l1_gather) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            umma::cp_async16_cg(stage + kATile + dst[i], src[i] + a.a_lo + c * 64, nbytes[i]);
+                            umma::cp_async16_ca(stage + dst[i], src[i] + a.a_hi + c * 64, nbytes[i]);
+                        if (!C32) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                umma::cp_async16_ca(stage + kATile + dst[i], src[i] + a.a_lo + c * 64, nbytes[i]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            umma::cp_async16_cg(stage + dst[i], src[i] + a.a_hi + c * 64, nbytes[i]);
+                        if (!C32) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                umma::cp_async16_cg(stage + kATile + dst[i], src[i] + a.a_lo + c * 64, nbytes[i]);
+                        }
                     }
                     umma::cp_async_arrive_noinc(&bar_full[st]);
                     if (++st == S) {
@@ -878,6 +871,9 @@ int sm_count() {
 template <bool C32, int KIND>
 void launch(const CUtensorMap& tmap, const KArgs& k, int grid, size_t smem, cudaStream_t s) {
     ASRB_CUDA(cudaFuncSetAttribute(gx_conv_kernel<C32, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (k.l1_gather)  // no more shared memory than the stages need: the remainder of the 228 KB serves as L1
+        ASRB_CUDA(cudaFuncSetAttribute(gx_conv_kernel<C32, KIND>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int)std::min<size_t>(100, (smem + 2048) * 100 / (228 * 1024) + 1)));
     gx_conv_kernel<C32, KIND><<<grid, kThreads, smem, s>>>(tmap, k);
     ASRB_CHECK_LAUNCH();
 }
@@ -904,6 +900,7 @@ void conv(const Plan& P, const ConvArgs& c, cudaStream_t s) {
     k.x = c.x.p;
     k.x_pitch = c.x.pitch;
     k.tma_gather = g_tma_gather;
+    k.l1_gather = g_l1_gather;
     k.a_hi = c.x.hi;
     k.a_lo = c.x.lo;
     k.chunks = c32 ? 1 : Cin / 64;
@@ -921,6 +918,7 @@ void conv(const Plan& P, const ConvArgs& c, cudaStream_t s) {
     k.stage_bytes = (c32 ? 1u : 2u) * kATile + k.chunk_bytes;
     k.tx_bytes = k.stage_bytes;
     k.stages = (int)std::max<size_t>(2, std::min<size_t>(8, (200 * 1024) / k.stage_bytes));
+    if (g_max_stages > 0) k.stages = std::max(2, std::min(k.stages, g_max_stages));
     const size_t smem = (size_t)k.stages * k.stage_bytes + 1024;
     k.wscale = ldexpf(1.f, -c.scale_exp);
     k.ncols = c.ncols;
@@ -999,12 +997,13 @@ namespace {
 // 8 channels per thread
 __global__ void __launch_bounds__(256)
 from_f32_kernel(const float* __restrict__ x, long long V, int C, int ldx, const float* __restrict__ row_scale,
-                __half* __restrict__ out, int pitch, int hi, int lo) {
+                const int32_t* __restrict__ rows, __half* __restrict__ out, int pitch, int hi, int lo) {
     const int c8 = C >> 3;
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= V * c8) return;
     const long long row = i / c8;
     const int col = (int)(i - row * c8) * 8;
+    const long long orow = rows ? rows[row] : row;  // input row `row` goes to output row rows[row]
     const float4 a = *reinterpret_cast<const float4*>(x + row * ldx + col);
     const float4 b = *reinterpret_cast<const float4*>(x + row * ldx + col + 4);
     float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -1014,7 +1013,7 @@ from_f32_kernel(const float* __restrict__ x, long long V, int C, int ldx, const 
         for (int j = 0; j < 8; ++j) v[j] *= s;
     }
     int overflow = 0;
-    split_store8(out + row * pitch + hi + col, out + row * pitch + lo + col, v, overflow);
+    split_store8(out + orow * pitch + hi + col, out + orow * pitch + lo + col, v, overflow);
     if (overflow) atomicOr(&g_overflow_flag, 1);
 }
 
@@ -1051,11 +1050,12 @@ static void zero_last_row(const H2View& v, cudaStream_t s) {
     ASRB_CUDA(cudaMemsetAsync(v.p + (size_t)(v.rows - 1) * v.pitch + v.lo, 0, (size_t)v.C * 2, s));
 }
 
-void from_f32(const float* x, int64_t V, int C, int ldx, const float* row_scale, H2View out, cudaStream_t s) {
-    ASRB_REQUIRE(C % 8 == 0 && ldx % 4 == 0 && out.C == C && out.rows == V + 1, "gx from_f32: bad shapes");
+void from_f32(const float* x, int64_t V, int C, int ldx, const float* row_scale, const int32_t* rows, H2View out,
+              cudaStream_t s) {
+    ASRB_REQUIRE(C % 8 == 0 && ldx % 4 == 0 && out.C == C && (rows || out.rows == V + 1), "gx from_f32: bad shapes");
     if (V > 0) {
-        from_f32_kernel<<<grid_for((size_t)V * (C / 8), 256), 256, 0, s>>>(x, V, C, ldx, row_scale, out.p, out.pitch, out.hi,
-                                                                          out.lo);
+        from_f32_kernel<<<grid_for((size_t)V * (C / 8), 256), 256, 0, s>>>(x, V, C, ldx, row_scale, rows, out.p, out.pitch,
+                                                                          out.hi, out.lo);
         ASRB_CHECK_LAUNCH();
     }
     zero_last_row(out, s);

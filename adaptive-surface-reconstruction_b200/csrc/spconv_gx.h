@@ -86,10 +86,14 @@ struct ConvArgs {
 size_t pairbuf_floats(const Plan& P, int ncols);
 void set_acc_groups(int g);
 void set_tma_gather(int v);
+void set_l1_gather(int v);
+void set_max_stages(int v);
 void conv(const Plan& P, const ConvArgs& a, cudaStream_t s);
 
 // format conversion and the elementwise helpers of the split-half format
-void from_f32(const float* x, int64_t V, int C, int ldx, const float* row_scale, H2View out, cudaStream_t s);
+// rows (may be null): input row i is written to output row rows[i] (only those rows of `out` are touched)
+void from_f32(const float* x, int64_t V, int C, int ldx, const float* row_scale, const int32_t* rows, H2View out,
+              cudaStream_t s);
 void to_f32(H2View x, int64_t V, float* out, int ldo, cudaStream_t s);
 void scale_rows(H2View x, int64_t V, const float* row_scale, H2View out, cudaStream_t s);
 int overflow_flag_read_and_clear(cudaStream_t s);  // 1 if any conversion saturated since the last call (synchronises)

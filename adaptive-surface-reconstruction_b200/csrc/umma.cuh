@@ -215,6 +215,10 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
 __device__ __forceinline__ void cp_async16_cg(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
 }
+// same, allocating in L1 (a row gathered again by the next kernel slots of the same tile can hit there)
+__device__ __forceinline__ void cp_async16_ca(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
 // the mbarrier receives one arrival (counted in its init count) when all cp.async issued so far
 // by this thread have landed
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* mbar) {

@@ -273,7 +273,6 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     _lib.lib()
     ops.SPARSE_CONV_BACKEND = args.backend
-    _lib.set_option("sparse_conv_output_stationary", args.conv_os)
     peaks = load_peaks()
 
     # N > 1: ONE cloud, the path sharded by output-voxel ranges across the ranks with a halo-row
@@ -335,7 +334,8 @@ def run_gpu(args):
     sizes = {"N": args.points,
              "V": [int(d["neighbors_row_splits%d" % i].shape[0] - 1) for i in range(args.levels)],
              "E": [int(d["neighbors_index%d" % i].shape[0]) for i in range(args.levels)],
-             "P": int(d["aggregation_neighbors_index"].shape[0]), "D": int(out["dual_vertex_indices"].shape[0]),
+             "P": int(d.get("aggregation_pairs_total", d["aggregation_neighbors_index"].shape[0])),
+             "D": int(out["dual_vertex_indices"].shape[0]),
              "M": int(out["vertices"].shape[0])}
     if args.verify and rank == 0:
         verify_geometry(args, cloud, out)
@@ -371,7 +371,7 @@ def run_gpu(args):
               "torch_alloc_retries_in_timed_region": mem1.get("num_alloc_retries", 0) - mem0.get("num_alloc_retries", 0),
               "torch_reserved_gb": round(mem1.get("reserved_bytes.all.current", 0) / 1e9, 2),
               "torch_peak_allocated_gb": round(mem1.get("allocated_bytes.all.peak", 0) / 1e9, 2),
-              "library_pool_reserved_gb": round(pool[0] / 1e9, 2), "library_pool_used_gb": round(pool[1] / 1e9, 2),
+              "library_pool_reserved_gb": round(pool[0] / 1e9, 2), "library_pool_used_high_gb": round(pool[3] / 1e9, 2),
               "library_pool_keeps_freed_memory": pool[2] > (1 << 60)}
     _lib.profile_enable(False)
     prof = _lib.profile_read()
@@ -503,7 +503,6 @@ def main():
     ap.add_argument("--backend", default="gx", choices=["gx", "tensor", "fp32"],
                     help="sparse-conv path: gx = split-half activations + TMA-gather tcgen05 kernel (default), "
                          "tensor = round-1 pair-major 3xTF32 kernel, fp32 = FMA kernel")
-    ap.add_argument("--conv-os", type=int, default=0, help="1: output-stationary kernel for the plain K=55 convs")
     ap.add_argument("--profile-run", action="store_true",
                     help="for runs under ncu: no minimum warm-up, no e2e leg; the printed numbers are NOT bench values")
     args = ap.parse_args()

@@ -43,8 +43,9 @@ int64_t asr_kernel_launches(void);
  * that carry no importance through the output-stationary tensor-core kernel (sparse_conv_os.cu). */
 int asr_set_option(const char* name, int value);
 
-/* bytes reserved / in use / release threshold of the stream-ordered memory pool the library allocates from */
-int asr_pool_stats(int64_t* reserved_bytes, int64_t* used_bytes, int64_t* release_threshold);
+/* bytes reserved / in use / release threshold / high-water mark in use of the stream-ordered memory pool the
+ * library allocates from (any pointer may be NULL) */
+int asr_pool_stats(int64_t* reserved_bytes, int64_t* used_bytes, int64_t* release_threshold, int64_t* used_high_bytes);
 /* Per-kernel device timing (CUDA events on the launching stream) for bench.py's
  * roofline figures: enable, run, then read (name, total ms, launches, algorithmic
  * flops) per instrumented kernel.  Reading synchronises the recorded events. */
@@ -91,6 +92,11 @@ int asr_grids_get(const asr_octree* tree, int level, uint64_t* d_voxel_keys, flo
  * (python: create_dual_vertex_indices, module.cpp:443): [num_duals, 8] leaf indices. */
 int asr_duals_count(asr_octree* tree, int64_t* num_duals, void* stream);
 int asr_duals_fill(asr_octree* tree, int64_t* d_dual_vertex_indices, void* stream);
+/* asynchronous form: _begin queues the counting pass on `stream` without a host synchronisation (a later
+ * asr_duals_count only waits for it); asr_duals_fill queues the fill; _check waits for the fill's error flag and
+ * returns status 2 ("found node is not a leaf", grid.cpp:436-440) — call it before trusting the result */
+int asr_duals_begin(asr_octree* tree, void* stream);
+int asr_duals_check(asr_octree* tree);
 
 /* ---------------------------------------------------------------- aggregation neighbours
  * replaces the Open3D MultiRadiusIndex/MultiRadiusSearch calls of
@@ -190,9 +196,11 @@ void asr_gx_plan_destroy(asr_gx_plan* plan);
 int64_t asr_gx_packed_filters_bytes(int kernel_size, int in_channels, int ncols);
 int asr_gx_pack_filters(const float* d_filters, int kernel_size, int in_channels, int out_channels, int col0, int ncols,
                         int scale_exp, void* d_packed, void* stream);
-/* fp32 [V, C] (row stride ldx) (* row_scale[row] if given) -> split-half view; also zeroes the view's zero row */
-int asr_gx_from_f32(const float* d_x, int64_t num_rows, int channels, int ldx, const float* d_row_scale, void* d_out,
-                    int out_pitch, int out_hi, int out_lo, void* stream);
+/* fp32 [num_rows, C] (row stride ldx) (* row_scale[row] if given) -> split-half view with out_rows rows; input row i
+ * goes to output row d_rows[i] (d_rows NULL: i, out_rows = num_rows); also zeroes the view's zero row (row out_rows) */
+int asr_gx_from_f32(const float* d_x, int64_t num_rows, int channels, int ldx, const float* d_row_scale,
+                    const int32_t* d_rows, int64_t out_rows, void* d_out, int out_pitch, int out_hi, int out_lo,
+                    void* stream);
 int asr_gx_to_f32(const void* d_x, int64_t num_rows, int channels, int pitch, int hi, int lo, float* d_out, int ldo,
                   void* stream);
 /* out = row_scale[row] * x, both split-half (the importance-weighted copy of SpecialSparseConv's conv1b input) */

@@ -37,11 +37,11 @@ def geom_checkers():
 
 @pytest.fixture(autouse=True)
 def _reset_kernel_options(request):
-    """GPU tests may switch the optional sparse-conv kernels on; restore the defaults."""
+    """GPU tests may change development knobs of the kernels; restore the defaults."""
     yield
     if "gpu" in request.keywords:
         import torch
         if torch.cuda.is_available():
             from asr_b200 import _lib
-            for name in ("sparse_conv_output_stationary", "sparse_conv_persistent"):
+            for name in ("gx_acc_groups", "gx_tma_gather", "gx_l1_gather", "gx_max_stages"):
                 _lib.set_option(name, 0)

@@ -99,14 +99,12 @@ def ref_with(imp, W, g, c, feats, idx, rs):
 
 @pytest.mark.parametrize("cin,cout", [(32, 64), (64, 128), (128, 32), (36, 56), (8, 8), (256, 256)])
 @pytest.mark.parametrize("level", [0, 1])
-@pytest.mark.parametrize("backend", ["tensor", "tensor_os", "tensor_pm", "fp32"])
+@pytest.mark.parametrize("backend", ["tensor", "fp32"])
 def test_sparse_conv_within_grid(cin, cout, level, backend, monkeypatch):
-    """tensor = per-tile tcgen05 kernel (default); tensor_os / tensor_pm = the optional
-    output-stationary / persistent pair-major tcgen05 kernels; fp32 = FMA tile kernel."""
+    """The generic entry point asr_sparse_conv (what the open3d:: shim runs): tensor = per-tile pair-major tcgen05
+    kernel (3xTF32); fp32 = FMA tile kernel.  The model's own path (gx) is covered by tests/test_gpu_gx.py."""
     from asr_b200 import _lib, ops
     from oracle import ops_cpu
-    _lib.set_option("sparse_conv_output_stationary", backend == "tensor_os")
-    _lib.set_option("sparse_conv_persistent", backend == "tensor_pm")
     monkeypatch.setattr(ops, "SPARSE_CONV_BACKEND", "tensor" if backend.startswith("tensor") else backend)
     c, t, grids = _scene(n=12000 if cin * cout > 20000 else 30000)
     g = grids[level]
@@ -146,7 +144,6 @@ def test_sparse_conv_within_grid(cin, cout, level, backend, monkeypatch):
                            normalize=True, normalize_col=0, normalizer=out_imp)
     assert (out2.cpu().double() - ref).abs().max() <= TOL
     # fused split conv: leading channels plain, trailing 8 importance-normalised
-    _lib.set_option("sparse_conv_output_stationary", 0)
     if cout >= 16:
         col = cout - 8
         out = ops.sparse_conv(plan, W.cuda(), x.cuda(), inp_importance=imp.cuda(), importance_col=col,

@@ -289,4 +289,16 @@ def test_traced_reference_archive_runs_on_the_cuda_shim():
     e_mirror = (code2 - code).abs().max().item()
     print("traced UNet5 on the CUDA shim: max|d feats| %.2e, max|d code| %.2e, max|d values| %.2e vs golden; "
           "max|d code| %.2e vs asr_b200.model.UNet" % (e_feats, e_code, e_val, e_mirror))
-    assert e_feats <= 1e-4 and e_code <= 1e-4 and e_val <= 1e-4 and e_mirror <= 1e-4
+    # the traced reference network (fp32 activations, round-1 3xTF32 kernels behind open3d::sparse_conv) against the
+    # golden outputs: 1e-4 abs; against the model mirror on the gx kernels (different summation order and operand
+    # split): 1e-4 relative to the code's magnitude
+    scale = max(1.0, float(np.abs(g["code"]).max()))
+    assert e_feats <= 1e-4 and e_code <= 1e-4 and e_val <= 1e-4 and e_mirror <= 1e-4 * scale
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, "r2_traced_reference_unet5_on_cuda_shim.json"), "w") as f:
+        import json
+        json.dump({"archive": "tests/golden/_local/ref_unet5_traced.pt (reference UNet5 traced by make_traced_archive.py)",
+                   "max_abs_err_aggregate_feats_vs_golden": float(e_feats), "max_abs_err_code_vs_golden": float(e_code),
+                   "max_abs_err_values_vs_golden": float(e_val), "max_abs_diff_code_vs_model_mirror_gx": float(e_mirror),
+                   "code_abs_max": scale}, f, indent=1)
