@@ -235,6 +235,13 @@ class LocalContext:
     def done(self, view, level):
         pass
 
+    def mark(self):
+        """allocation mark / release of everything allocated after it (arena contexts; torch frees by itself)"""
+        return None
+
+    def release(self, mark):
+        pass
+
     def plans(self, input_dict, levels):
         return build_plans(input_dict, levels)
 
@@ -244,6 +251,10 @@ def run_block(block, x, plan, importance, scratch, out=None, out_f32=None, res=N
     ctx = ctx or LocalContext()
     first, firstb, rest = _block_filters(block)
     out_imp = None
+    if out is None and out_f32 is None:
+        # the block's result is allocated before its temporaries, which are released at the end of the block
+        out = ctx.empty(plan.table_rows, _ncols(rest[-1] if rest else first), x.buf.device)
+    mark = ctx.mark()
     last = not rest
     y = conv(plan, x, first, out=out if last else None, out_f32=out_f32 if last else None,
              res=res if last else None, scratch=scratch, alloc=ctx.empty)
@@ -263,6 +274,7 @@ def run_block(block, x, plan, importance, scratch, out=None, out_f32=None, res=N
                  scratch=scratch, alloc=ctx.empty)
         if isinstance(y, H2):
             ctx.done(y, level)
+    ctx.release(mark)
     return y, out_imp
 
 

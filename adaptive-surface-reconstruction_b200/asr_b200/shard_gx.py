@@ -72,6 +72,7 @@ class Arena:
         if start + n > self.nbytes:
             raise RuntimeError("asr_b200 shard arena exhausted: need %d more bytes (ASR_SHARD_ARENA_GB)" % (start + n - self.nbytes))
         self.off = start + n
+        self.peak = max(getattr(self, "peak", 0), self.off)
         return self.buf[start:start + n].view(dtype).view(*shape)
 
     def offset_of(self, t):
@@ -140,6 +141,15 @@ class ShardContext(gx.LocalContext):
         buf = self.arena.alloc((V + 1, 2 * C_), torch.float16)
         buf[V:].zero_()
         return gx.H2(buf, C_, 0, C_)
+
+    def mark(self):
+        return self.arena.off
+
+    def release(self, mark):
+        # buffers allocated after `mark` were temporaries of a block: every rank has passed the barrier that followed
+        # the last push into them before anything is allocated there again (the next convolution's output)
+        self.arena.off = mark
+        self.arena.peak = max(getattr(self.arena, "peak", 0), mark)
 
     def plans(self, input_dict, levels):
         cache = input_dict.get("_asr_gx_shard_plans")

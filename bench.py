@@ -318,6 +318,7 @@ def run_gpu(args):
         # the sharded result against the single-GPU path on the same cloud (rank 0 runs it once, untimed)
         barrier()
         if rank == 0:
+            torch.cuda.empty_cache()
             saved_k = net.K
             net.K = ops
             one = pipeline.reconstruct_vertices(net, devt["points"], devt["normals"], devt["radii"], bb[0], bb[1])
@@ -329,6 +330,7 @@ def run_gpu(args):
                                              torch.equal(one["vertices"], out["vertices"])),
                       "vertices": int(one["vertices"].shape[0])}
             del one
+            torch.cuda.empty_cache()
         barrier()
     d = out["input_dict"]
     sizes = {"N": args.points,
