@@ -49,6 +49,10 @@ void set_l1_gather(int v) { g_l1_gather = v != 0; }
 void set_max_stages(int v) { g_max_stages = v; }
 static int g_acc_groups = 0;  // dev knob: main-accumulator groups per TMEM buffer (0 = as many as fit, <= 4)
 void set_acc_groups(int g) { g_acc_groups = g; }
+// dev knob for ABLATION TIMINGS ONLY (results become garbage): bit 0 no filter copies, 1 no pair-buffer reads,
+// 2 no row gathers, 3 no output stores, 4 no MMAs
+static int g_ablate = 0;
+void set_ablate(int v) { g_ablate = v; }
 
 namespace {
 constexpr int kRowBlockShift = 15;  // rare entries are grouped by blocks of 2^15 output rows
@@ -397,7 +401,7 @@ struct KArgs {
     const __half* x;
     int x_pitch;
     int a_hi, a_lo, chunks;
-    int tma_gather, l1_gather;
+    int tma_gather, l1_gather, ablate;
     // filters
     const uint8_t* wp;
     unsigned long long slot_bytes;
@@ -574,7 +578,9 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                 for (int c = 0; c < a.chunks; ++c) {
                     umma::mbar_wait(&bar_empty[st], ph ^ 1);
                     const uint32_t stage = sbase + (uint32_t)st * a.stage_bytes;
-                    if (warp == 0 && lane == 0) {
+                    if (warp == 0 && lane == 0 && (a.ablate & 1)) {
+                        umma::mbar_arrive(&bar_full[st]);
+                    } else if (warp == 0 && lane == 0) {
                         const uint32_t bdst = stage + (C32 ? 1u : 2u) * kATile;
                         umma::mbar_arrive_expect_tx(&bar_full[st], a.chunk_bytes);
                         asm volatile(
@@ -582,7 +588,8 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                                 "l"(wsrc + (size_t)c * a.chunk_bytes), "r"(a.chunk_bytes), "r"(umma::smem_u32(&bar_full[st]))
                                 : "memory");
                     }
-                    if (a.l1_gather) {
+                    if (a.ablate & 4) {
+                    } else if (a.l1_gather) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
                             umma::cp_async16_ca(stage + dst[i], src[i] + a.a_hi + c * 64, nbytes[i]);
@@ -634,7 +641,8 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                         const uint32_t acc = acc0 + (uint32_t)(g * 2 * N), cor = acc + (uint32_t)N;
                         uint32_t first = (started >> g) & 1u, firstc = first;
                         started |= 1u << g;
-                        if (C32) {
+                        if (a.ablate & 16) {
+                        } else if (C32) {
                             // one A tile [hi 32 | lo 32], one B tile [hi 32 | lo 32]: k-steps 0,1 = hi, 2,3 = lo
                             const uint64_t da = dbase + (stage >> 4), db = dbase + ((stage + kATile) >> 4);
 #pragma unroll
@@ -703,7 +711,7 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                 const long long v = (long long)tile * kTM + L;
                 if (v < a.V) {
                     row = a.row_map ? a.row_map[v] : v;
-                    if (a.rare_rs) {
+                    if (a.rare_rs && !(a.ablate & 2)) {
                         r0 = a.rare_rs[v];
                         r1 = a.rare_rs[v + 1];
                     }
@@ -770,7 +778,7 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                 }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], a.wscale, 0.f);
-                if (row < 0 || n0 >= a.ncols) continue;
+                if (row < 0 || n0 >= a.ncols || (a.ablate & 8)) continue;
                 if (KIND == kKindPairBuf) {
                     float4* dst = reinterpret_cast<float4*>(a.pair_out + (size_t)row * N + n0);
 #pragma unroll
@@ -901,6 +909,7 @@ void conv(const Plan& P, const ConvArgs& c, cudaStream_t s) {
     k.x_pitch = c.x.pitch;
     k.tma_gather = g_tma_gather;
     k.l1_gather = g_l1_gather;
+    k.ablate = g_ablate;
     k.a_hi = c.x.hi;
     k.a_lo = c.x.lo;
     k.chunks = c32 ? 1 : Cin / 64;

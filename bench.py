@@ -42,11 +42,12 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
-def conv_traffic_per_launch():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the sparse-conv tile kernel, from the
+def conv_traffic_per_launch(backend="gx"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the sparse-conv kernel of `backend`, from the
     committed ncu capture of this workload (profiles/, latest round); None if there is none."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_sparse_conv_tc_traffic.json")))
+    name = {"gx": "r*_gx_conv_traffic.json", "tensor": "r*_sparse_conv_tc_traffic.json"}.get(backend)
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", name))) if name else []
     if not files:
         return None
     with open(files[-1]) as f:
@@ -417,7 +418,7 @@ def run_gpu(args):
         roofline = {
             "bound": "tensor", "kernel": {"gx": "gx_conv_kernel", "tensor": "sparse_conv_tc_kernel"}.get(ops.SPARSE_CONV_BACKEND, "sparse_conv_tile_kernel"),
             "achieved": achieved, "peak": peak,
-            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": conv_traffic_per_launch(),
+            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": conv_traffic_per_launch(ops.SPARSE_CONV_BACKEND),
             "peak_source": "%s bf16 dense, sustained (kernel timed inside a long step)" % peaks["source"],
             "note": {"gx": "tcgen05.mma kind::f16 on fp16 hi/lo halves of fp32 values: 3 tensor-pipe flops per algorithmic flop at "
                            "the bf16/fp16 rate (1/3 of the peak is this scheme's ceiling); both launches of a convolution "
