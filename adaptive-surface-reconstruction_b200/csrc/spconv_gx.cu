@@ -53,13 +53,18 @@ void set_acc_groups(int g) { g_acc_groups = g; }
 // 2 no row gathers, 3 no output stores, 4 no MMAs
 static int g_ablate = 0;
 void set_ablate(int v) { g_ablate = v; }
+static int g_single_tmem = 0;  // dev knob: one TMEM buffer with two accumulator groups for N > 64
+void set_single_tmem(int v) { g_single_tmem = v != 0; }
 
 namespace {
 constexpr int kRowBlockShift = 15;  // rare entries are grouped by blocks of 2^15 output rows
 constexpr int kProducerWarps = 4;
 constexpr int kMmaWarp = kProducerWarps;                  // warps 0-3 gather, warp 4 MMA, warps 5-12 epilogue
 constexpr int kEpilogueWarps = 8;                         // two per TMEM lane quarter, half of the columns each
-constexpr int kThreads = (kProducerWarps + 1 + kEpilogueWarps) * 32;
+constexpr int kRareWarp0 = kProducerWarps + 1 + kEpilogueWarps;  // warps 13-16 sum the rare entries of the tile's rows
+constexpr int kRareWarps = 4;
+constexpr int kRingWarp = kRareWarp0 + kRareWarps;  // warp 17: one thread feeds the pair-buffer ring
+constexpr int kThreads = (kRingWarp + 1) * 32;
 constexpr uint32_t kATile = kTM * 128;  // 128 rows x 128 bytes
 
 __device__ int g_overflow_flag = 0;
@@ -409,6 +414,8 @@ struct KArgs {
     // MMA shape
     int N, ncat, stages;
     int G, nbuf, by_slot;  // accumulator groups per TMEM buffer, buffers, group = kernel slot (importance variant)
+    int nrb, rare_lp;      // staging tiles (1 or 2), lanes per pair row of the rare warps (power of two >= N / 4)
+    int ring_slots, ring_pairs;  // pair-buffer ring: chunks of ring_pairs pair rows
     // importance variant (conv1b of SpecialSparseConv): every gathered row is weighted by imp[input row]
     const float* imp;
     const int32_t* rare_in;  // [R] input row of every rare entry (row-major rare order)
@@ -451,8 +458,12 @@ __device__ __forceinline__ void split_store8(__half* hi_p, __half* lo_p, const f
 template <bool C32, int KIND>
 __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_constant__ CUtensorMap tmap, const KArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ uint64_t bar_full[8], bar_empty[8], bar_tfull[2], bar_tempty[2];
+    __shared__ uint64_t bar_full[8], bar_empty[8], bar_tfull[2], bar_tempty[2], bar_rfull[2], bar_rempty[2];
     __shared__ uint32_t tmem_slot;
+    __shared__ uint64_t bar_ring_full[4], bar_ring_empty[4];
+    __shared__ long long s_rs[2][kTM + 1];      // rare-segment bounds of the tile's rows
+    __shared__ float s_w[kRareWarps][32];       // importance of the pairs of a ring chunk
+    __shared__ int s_dst[kTM];                  // destination row of every staging row
     const uint32_t sbase = (umma::smem_u32(smem_raw) + 1023u) & ~1023u;  // operand tiles need 1024-byte alignment
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = a.stages;
@@ -481,6 +492,12 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
             for (int i = 0; i < 2; ++i) {
                 umma::mbar_init(&bar_tfull[i], 1);
                 umma::mbar_init(&bar_tempty[i], kEpilogueWarps);
+                umma::mbar_init(&bar_rfull[i], kRareWarps);
+                umma::mbar_init(&bar_rempty[i], kEpilogueWarps);
+            }
+            for (int i = 0; i < 4; ++i) {
+                umma::mbar_init(&bar_ring_full[i], 1);
+                umma::mbar_init(&bar_ring_empty[i], kRareWarps);
             }
             umma::fence_barrier_init();
         }
@@ -688,34 +705,38 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
             }
         }
         __syncwarp();
-    } else {
+    } else if (warp < kRareWarp0) {
         // ------------------------------------------------------------------ epilogue
         // 8 warps: warp e reads TMEM lane quarter e % 4 (thread = output row / pair) and handles half e / 4 of the
-        // columns (<= 64).  The contribution of the row's rare entries does not depend on this tile's MMAs, so it is
-        // summed from the pair buffer BEFORE the wait on the accumulator (all 16-byte loads of a pair row in flight
-        // at once) and overlaps the main loop; afterwards the accumulator groups are added, the epilogue applied and
-        // the row written.
+        // columns (<= 64).  All global traffic of the epilogue is COALESCED through a shared-memory staging tile
+        // (the LSU processes one 128-byte line per cycle: a thread-per-row store or load costs 32 line transactions
+        // per warp instruction, and those — not the gathers — bounded the first version of this kernel, see
+        // profiles/r2_gx_ablation.txt):
+        //   1. the rare warps have summed the row's pair-buffer segment into the staging row -> registers;
+        //   2. accumulator groups are added, the epilogue applied, the result written back to the staging row in its
+        //      final memory image ([hi halves | lo halves], or fp32);
+        //   3. the two warps of the lane quarter copy their 32 rows out, consecutive lanes = consecutive 16 bytes.
         const int e = warp - (kMmaWarp + 1);
         const int q = warp & 3;  // TMEM lane quarter this warp may access (warps 5..12 -> 1,2,3,0,1,2,3,0)
         const int L = q * 32 + lane;
         const int half = e >> 2;
+        const int tp = half * 32 + lane;  // thread of the quarter's warp pair
         const int cph = ((N / 16 + 1) / 2) * 16;  // columns of half 0 (multiple of 16)
         const int c0 = half ? cph : 0, c1 = half ? N : cph;
+        const bool has_rare = KIND == kKindStationary && a.rare_rs != nullptr && !(a.ablate & 2);
+        const uint32_t ldr = 4u * (uint32_t)N + 16u;  // staging row pitch in bytes (+16: conflict-free thread-per-row access)
+        uint8_t* const stage_gen = smem_raw + (sbase - umma::smem_u32(smem_raw)) + (size_t)S * a.stage_bytes;
+        const int nrb = a.nrb;
         int overflow = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const int buf = it % nbuf;
-            long long row = -1;       // output row (final kinds) / pair-buffer row
-            long long r0 = 0, r1 = 0;  // rare segment of the row
+            const int buf = it % nbuf, rb = it % nrb;
+            uint8_t* const Rb = stage_gen + (size_t)rb * kTM * ldr;
+            uint8_t* const myrow = Rb + (size_t)L * ldr;
+            long long row = -1;  // output row (final kinds) / pair-buffer row
             if (KIND == kKindStationary) {
                 const long long v = (long long)tile * kTM + L;
-                if (v < a.V) {
-                    row = a.row_map ? a.row_map[v] : v;
-                    if (a.rare_rs && !(a.ablate & 2)) {
-                        r0 = a.rare_rs[v];
-                        r1 = a.rare_rs[v + 1];
-                    }
-                }
+                if (v < a.V) row = a.row_map ? a.row_map[v] : v;
             } else {
                 row = a.out_pos[(size_t)tile * kTM + L];
             }
@@ -734,27 +755,9 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                     }
                 }
             }
-            // rare entries of this row, columns [c0, c1): <= 64 floats in registers
-            float racc[64];
-#pragma unroll
-            for (int j = 0; j < 64; ++j) racc[j] = 0.f;
-            if (KIND == kKindStationary) {
-                for (long long p = r0; p < r1; ++p) {
-                    const float4* src = reinterpret_cast<const float4*>(a.pairbuf + (size_t)p * N + c0);
-                    const float w = a.imp ? a.imp[a.rare_in[p]] : 1.f;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (c0 + 4 * j < c1) {
-                            const float4 t = __ldg(src + j);
-                            racc[4 * j] = fmaf(t.x, w, racc[4 * j]);
-                            racc[4 * j + 1] = fmaf(t.y, w, racc[4 * j + 1]);
-                            racc[4 * j + 2] = fmaf(t.z, w, racc[4 * j + 2]);
-                            racc[4 * j + 3] = fmaf(t.w, w, racc[4 * j + 3]);
-                        }
-                    }
-                }
-            }
-            __syncwarp();
+            // the sums of the rows' rare entries are in the staging tile (columns [c0, c1) of a row are touched by
+            // this thread only: they are read block by block below and replaced by the block's results)
+            if (has_rare) umma::mbar_wait(&bar_rfull[rb], (it / nrb) & 1);
             umma::mbar_wait(&bar_tfull[buf], (it / nbuf) & 1);
             umma::tc_fence_after();
             const uint32_t t_acc = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * accw);
@@ -778,17 +781,25 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                 }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], a.wscale, 0.f);
-                if (row < 0 || n0 >= a.ncols || (a.ablate & 8)) continue;
+                if (n0 >= a.ncols && KIND != kKindPairBuf) continue;  // warp-uniform
+                float4* const blk = reinterpret_cast<float4*>(myrow + 4 * n0);  // this block's 64 bytes of the staging row
                 if (KIND == kKindPairBuf) {
-                    float4* dst = reinterpret_cast<float4*>(a.pair_out + (size_t)row * N + n0);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    for (int j = 0; j < 4; ++j) blk[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     continue;
                 }
+                if (has_rare) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += racc[16 * cb + j];
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 t = blk[j];
+                        v[4 * j] += t.x;
+                        v[4 * j + 1] += t.y;
+                        v[4 * j + 2] += t.z;
+                        v[4 * j + 3] += t.w;
+                    }
+                }
                 const int nvalid = min(16, a.ncols - n0);  // multiple of 8
-                if (KIND != kKindPairBuf && a.norm && nrm != 0.f) {
+                if (a.norm && nrm != 0.f) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] /= nrm;
                 }
@@ -797,7 +808,7 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                     if (a.bias && j < nvalid) v[j] += a.bias[n0 + j];
                     if (a.relu) v[j] = fmaxf(v[j], 0.f);
                 }
-                if (a.res) {
+                if (a.res && row >= 0) {
                     const __half* rh = a.res + (size_t)row * a.res_pitch + a.res_hi + n0;
                     const __half* rl = a.res + (size_t)row * a.res_pitch + a.res_lo + n0;
                     for (int j0 = 0; j0 < nvalid; j0 += 8) {
@@ -810,20 +821,183 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                     }
                 }
                 if (a.out_f) {
-                    float* dst = a.out_f + (size_t)row * a.out_f_pitch + n0;
-                    for (int j0 = 0; j0 < nvalid; j0 += 4)
-                        *reinterpret_cast<float4*>(dst + j0) = make_float4(v[j0], v[j0 + 1], v[j0 + 2], v[j0 + 3]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) blk[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 } else {
-                    __half* oh = a.out_h + (size_t)row * a.out_pitch + a.out_hi + n0;
-                    __half* ol = a.out_h + (size_t)row * a.out_pitch + a.out_lo + n0;
-                    for (int j0 = 0; j0 < nvalid; j0 += 8) split_store8(oh + j0, ol + j0, v + j0, overflow);
+                    // split-half image of the block, in place: [16 hi halves | 16 lo halves]
+                    __half* oh = reinterpret_cast<__half*>(blk);
+                    int of = 0;
+                    split_store8(oh, oh + 16, v, of);
+                    split_store8(oh + 8, oh + 24, v + 8, of);
+                    if (row >= 0) overflow |= of;
                 }
             }
             umma::tc_fence_before();
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(&bar_tempty[buf]);
+            if (half == 0) s_dst[L] = (a.ablate & 8) ? -1 : (int)row;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+            // copy-out of rows q * 32 .. q * 32 + 31: chunk = 16 bytes, consecutive threads = consecutive chunks of a row
+            {
+                const int CH = (KIND == kKindPairBuf ? N : a.ncols) >> 2;  // chunks per row
+                const int hc = CH >> 1;                                   // per plane of the split-half format
+                for (int idx = tp; idx < 32 * CH; idx += 64) {
+                    const int r = idx / CH, ch = idx - r * CH;
+                    const int drow = s_dst[q * 32 + r];
+                    if (drow < 0) continue;
+                    const uint8_t* src = Rb + (size_t)(q * 32 + r) * ldr;
+                    uint8_t* dst;
+                    if (KIND == kKindPairBuf) {
+                        dst = reinterpret_cast<uint8_t*>(a.pair_out + (size_t)drow * N) + ch * 16;
+                        src += ch * 16;
+                    } else if (a.out_f) {
+                        dst = reinterpret_cast<uint8_t*>(a.out_f + (size_t)drow * a.out_f_pitch) + ch * 16;
+                        src += ch * 16;
+                    } else {
+                        // columns 8 cc .. 8 cc + 7 of plane `plane`: block cc / 2 of the row, second half of it if cc is odd
+                        const int plane = ch >= hc ? 1 : 0, cc = ch - plane * hc;
+                        dst = reinterpret_cast<uint8_t*>(a.out_h + (size_t)drow * a.out_pitch + (plane ? a.out_lo : a.out_hi)) + cc * 16;
+                        src += (cc >> 1) * 64 + plane * 32 + (cc & 1) * 16;
+                    }
+                    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+                }
+            }
+            if (has_rare) {
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&bar_rempty[rb]);
+            }
         }
         if (overflow) atomicOr(&g_overflow_flag, 1);
+    } else if (warp == kRingWarp) {
+        // ------------------------------------------------------------------ pair-buffer ring producer (one thread of
+        // its own warp: as a second lane of the MMA warp it was starved by that warp's barrier polling)
+        if (lane == 0 && KIND == kKindStationary && a.rare_rs != nullptr && !(a.ablate & 2)) {
+            // pair-buffer ring producer: the tiles' rare segments, chunk by chunk, with bulk copies
+            const uint32_t ldr = 4u * (uint32_t)N + 16u;
+            const uint32_t ring = sbase + (uint32_t)S * a.stage_bytes + (uint32_t)a.nrb * kTM * ldr;
+            const int CP = a.ring_pairs, RS = a.ring_slots;
+            const uint32_t slot_bytes = (uint32_t)CP * N * 4;
+            int rsl = 0, rph = 0;
+            long long n0 = 0, n1 = 0;
+            if ((int)blockIdx.x < ntiles) {
+                const long long t0 = (long long)blockIdx.x * kTM;
+                n0 = a.rare_rs[t0];
+                n1 = a.rare_rs[min(t0 + kTM, (long long)a.V)];
+            }
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const long long tp0 = n0, tp1 = n1;
+                if (tile + (int)gridDim.x < ntiles) {  // bounds of the next tile while this one streams
+                    const long long t0 = (long long)(tile + gridDim.x) * kTM;
+                    n0 = a.rare_rs[t0];
+                    n1 = a.rare_rs[min(t0 + kTM, (long long)a.V)];
+                }
+                for (long long c = tp0; c < tp1; c += CP) {
+                    const uint32_t bytes = (uint32_t)min((long long)CP, tp1 - c) * (uint32_t)N * 4u;
+                    umma::mbar_wait(&bar_ring_empty[rsl], rph ^ 1);
+                    umma::mbar_arrive_expect_tx(&bar_ring_full[rsl], bytes);
+                    asm volatile(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ring + (uint32_t)rsl * slot_bytes),
+                            "l"(a.pairbuf + (size_t)c * N), "r"(bytes), "r"(umma::smem_u32(&bar_ring_full[rsl]))
+                            : "memory");
+                    if (++rsl == RS) {
+                        rsl = 0;
+                        rph ^= 1;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ rare-entry sums (stationary kind)
+        // The products of a tile's rare entries are ONE contiguous piece of the pair buffer (row order).  The ring
+        // warp streams it through a small ring of shared-memory chunks with bulk copies (cp.async.bulk: no
+        // LSU transactions, deep memory-level parallelism from one instruction); a group of LP = N / 4 lanes of
+        // these warps owns every (128 / LP)-th row and adds their pairs per row IN PAIR ORDER (the order of the
+        // single-threaded sum it replaces: results are bit-identical) from the ring into the staging tile.
+        const bool has_rare = KIND == kKindStationary && a.rare_rs != nullptr && !(a.ablate & 2);
+        if (has_rare) {
+            const int rw = warp - kRareWarp0;
+            const int rt = rw * 32 + lane;  // thread of the four rare warps
+            const int LP = a.rare_lp;
+            const int NG = kTM / LP;            // lane groups; group g owns rows g, g + NG, g + 2 NG, ... so that the
+            const int g = rt / LP;              // pairs of one ring chunk (consecutive rows) spread over all groups
+            const int lig = lane & (LP - 1);
+            const bool colok = 4 * lig < N;
+            const uint32_t ldr = 4u * (uint32_t)N + 16u;
+            uint8_t* const stage_gen = smem_raw + (sbase - umma::smem_u32(smem_raw)) + (size_t)S * a.stage_bytes;
+            const int nrb = a.nrb;
+            const float* const ring = reinterpret_cast<const float*>(stage_gen + (size_t)nrb * kTM * ldr);
+            const int CP = a.ring_pairs, RS = a.ring_slots;
+            int rsl = 0, rph = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int rb = it % nrb;
+                uint8_t* const Rb = stage_gen + (size_t)rb * kTM * ldr;
+                const long long t0 = (long long)tile * kTM;
+                long long* const rs = s_rs[it & 1];  // rare-segment bounds of the tile's rows (double-buffered: one barrier per tile)
+                rs[rt] = a.rare_rs[min(t0 + rt, (long long)a.V)];
+                if (rt == 0) rs[kTM] = a.rare_rs[min(t0 + kTM, (long long)a.V)];
+                asm volatile("bar.sync 5, 128;" ::: "memory");
+                const long long tp0 = rs[0], tp1 = rs[kTM];
+                umma::mbar_wait(&bar_rempty[rb], ((it / nrb) & 1) ^ 1);
+                int cr = g;  // current row
+                long long p = rs[cr], pe = rs[cr + 1];
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                auto finish_row = [&]() {
+                    if (colok) *reinterpret_cast<float4*>(Rb + (size_t)cr * ldr + 16 * lig) = acc;
+                    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    cr += NG;
+                    if (cr < kTM) {
+                        p = rs[cr];
+                        pe = rs[cr + 1];
+                    }
+                };
+                for (long long c = tp0; c < tp1; c += CP) {
+                    const long long ce = min(c + CP, tp1);
+                    if (a.imp) {  // importance of the chunk's pairs (one per lane; CP <= 32), fetched while the chunk lands
+                        __syncwarp();
+                        s_w[rw][lane] = c + lane < ce ? a.imp[a.rare_in[c + lane]] : 0.f;
+                        __syncwarp();
+                    }
+                    umma::mbar_wait(&bar_ring_full[rsl], rph);
+                    const float* const chunk = ring + (size_t)rsl * CP * N;
+                    while (cr < kTM && p < ce) {
+                        const long long hi = min(pe, ce);
+                        while (p < hi) {
+                            float4 t[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                t[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (p + u < hi && colok)
+                                    t[u] = *reinterpret_cast<const float4*>(chunk + (size_t)(p + u - c) * N + 4 * lig);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (p + u < hi) {
+                                    const float w = a.imp ? s_w[rw][p + u - c] : 1.f;
+                                    acc.x = fmaf(t[u].x, w, acc.x);
+                                    acc.y = fmaf(t[u].y, w, acc.y);
+                                    acc.z = fmaf(t[u].z, w, acc.z);
+                                    acc.w = fmaf(t[u].w, w, acc.w);
+                                }
+                            }
+                            p = min(p + 4, hi);
+                        }
+                        if (p < pe) break;  // the row continues in the next chunk
+                        finish_row();
+                    }
+                    __syncwarp();
+                    if (lane == 0) umma::mbar_arrive(&bar_ring_empty[rsl]);
+                    if (++rsl == RS) {
+                        rsl = 0;
+                        rph ^= 1;
+                    }
+                }
+                while (cr < kTM) finish_row();  // rows without (further) pairs
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&bar_rfull[rb]);
+            }
+        }
     }
     umma::tc_fence_before();
     __syncthreads();
@@ -921,14 +1095,28 @@ void conv(const Plan& P, const ConvArgs& c, cudaStream_t s) {
     k.ncat = (!c32 && N <= 128) ? 1 : 0;  // [B_hi | B_lo] as one operand of width 2 N <= 256
     // accumulator groups (see the kernel): as many as fit next to a second buffer, at most 4
     k.by_slot = 0;
-    k.nbuf = N <= 64 ? 2 : 1;
+    // two TMEM buffers whenever [main N | corr N] fits twice (the epilogue of a tile then overlaps the next tile's
+    // MMAs; for N = 128 that leaves one accumulator group); dev knob gx_single_tmem: round-2a policy (N > 64: one
+    // buffer, two groups)
+    k.nbuf = (g_single_tmem && N > 64) ? 1 : (2 * N * 2 <= 512 ? 2 : 1);
     k.G = std::max(1, std::min(g_acc_groups > 0 ? g_acc_groups : 4, 512 / (2 * N * k.nbuf)));
+    k.rare_lp = 4;
+    while (k.rare_lp * 4 < N) k.rare_lp <<= 1;
     k.zero_row = (int)P.V_in;
     k.stage_bytes = (c32 ? 1u : 2u) * kATile + k.chunk_bytes;
     k.tx_bytes = k.stage_bytes;
-    k.stages = (int)std::max<size_t>(2, std::min<size_t>(8, (200 * 1024) / k.stage_bytes));
+    // shared memory: pipeline stages + 1-2 staging tiles of 128 x (4 N + 16) bytes (rare sums in, results out);
+    // the gathers need little depth (2 stages measure the same as 4), so the staging tiles come first
+    const size_t budget = 222 * 1024, stage_tile = (size_t)kTM * (4 * N + 16);
+    const bool ring = P.mode == kModeStationary && P.R > 0;  // the stationary pass reads the pair buffer through a ring
+    k.ring_pairs = (int)std::min<size_t>(32, 8192 / (4 * N));
+    k.ring_slots = ring ? (N > 64 ? 3 : 4) : 0;
+    const size_t ring_bytes = (size_t)k.ring_slots * k.ring_pairs * N * 4;
+    k.nrb = (budget - ring_bytes - 2 * stage_tile) / k.stage_bytes >= 2 ? 2 : 1;
+    k.stages = (int)std::max<size_t>(2, std::min<size_t>(8, (budget - ring_bytes - k.nrb * stage_tile) / k.stage_bytes));
     if (g_max_stages > 0) k.stages = std::max(2, std::min(k.stages, g_max_stages));
-    const size_t smem = (size_t)k.stages * k.stage_bytes + 1024;
+    const size_t smem = (size_t)k.stages * k.stage_bytes + k.nrb * stage_tile + ring_bytes + 1024;
+    ASRB_REQUIRE(smem <= 227 * 1024 - 4096, "gx conv: shared-memory budget exceeded");  // 4 KB static (barriers, row bounds)
     k.wscale = ldexpf(1.f, -c.scale_exp);
     k.ncols = c.ncols;
     const CUtensorMap tmap = make_row_map(c.x);
