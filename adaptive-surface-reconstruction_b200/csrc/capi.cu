@@ -113,6 +113,7 @@ int asr_set_option(const char* name, int value) {
         else if (std::string(name) == "gx_max_stages") gx::set_max_stages(value);
         else if (std::string(name) == "gx_ablate") gx::set_ablate(value);
         else if (std::string(name) == "gx_single_tmem") gx::set_single_tmem(value);
+        else if (std::string(name) == "gx_one_team") gx::set_one_team(value);
         else if (std::string(name) == "tc_stages") sparse_conv_tc_tune(value, 0);
         else if (std::string(name) == "tc_row_groups") sparse_conv_tc_tune(0, value);
         else throw Error(kInvalidArgument, std::string("unknown option: ") + name);

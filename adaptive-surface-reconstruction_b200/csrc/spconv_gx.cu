@@ -53,6 +53,8 @@ void set_acc_groups(int g) { g_acc_groups = g; }
 // 2 no row gathers, 3 no output stores, 4 no MMAs
 static int g_ablate = 0;
 void set_ablate(int v) { g_ablate = v; }
+static int g_one_team = 0;     // dev knob: one epilogue team even where two fit
+void set_one_team(int v) { g_one_team = v != 0; }
 static int g_single_tmem = 0;  // dev knob: one TMEM buffer with two accumulator groups for N > 64
 void set_single_tmem(int v) { g_single_tmem = v != 0; }
 
@@ -62,7 +64,7 @@ constexpr int kProducerWarps = 4;
 constexpr int kMmaWarp = kProducerWarps;                  // warps 0-3 gather, warp 4 MMA, warps 5-12 epilogue
 constexpr int kEpilogueWarps = 8;                         // two per TMEM lane quarter, half of the columns each
 constexpr int kRareWarp0 = kProducerWarps + 1 + kEpilogueWarps;  // warps 13-16 sum the rare entries of the tile's rows
-constexpr int kRareWarps = 4;
+constexpr int kRareWarps = 6;
 constexpr int kRingWarp = kRareWarp0 + kRareWarps;  // warp 17: one thread feeds the pair-buffer ring
 constexpr int kThreads = (kRingWarp + 1) * 32;
 constexpr uint32_t kATile = kTM * 128;  // 128 rows x 128 bytes
@@ -414,6 +416,7 @@ struct KArgs {
     // MMA shape
     int N, ncat, stages;
     int G, nbuf, by_slot;  // accumulator groups per TMEM buffer, buffers, group = kernel slot (importance variant)
+    int teams;             // epilogue teams (1 or 2)
     int nrb, rare_lp;      // staging tiles (1 or 2), lanes per pair row of the rare warps (power of two >= N / 4)
     int ring_slots, ring_pairs;  // pair-buffer ring: chunks of ring_pairs pair rows
     // importance variant (conv1b of SpecialSparseConv): every gathered row is weighted by imp[input row]
@@ -458,12 +461,11 @@ __device__ __forceinline__ void split_store8(__half* hi_p, __half* lo_p, const f
 template <bool C32, int KIND>
 __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_constant__ CUtensorMap tmap, const KArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ uint64_t bar_full[8], bar_empty[8], bar_tfull[2], bar_tempty[2], bar_rfull[2], bar_rempty[2];
+    __shared__ uint64_t bar_full[8], bar_empty[8], bar_tfull[4], bar_tempty[4], bar_rfull[2], bar_rempty[2];
     __shared__ uint32_t tmem_slot;
     __shared__ uint64_t bar_ring_full[4], bar_ring_empty[4];
     __shared__ long long s_rs[2][kTM + 1];      // rare-segment bounds of the tile's rows
     __shared__ float s_w[kRareWarps][32];       // importance of the pairs of a ring chunk
-    __shared__ int s_dst[kTM];                  // destination row of every staging row
     const uint32_t sbase = (umma::smem_u32(smem_raw) + 1023u) & ~1023u;  // operand tiles need 1024-byte alignment
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = a.stages;
@@ -489,11 +491,13 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                 umma::mbar_init(&bar_full[i], a.tma_gather ? 1 : kProducerWarps * 32 + 1);
                 umma::mbar_init(&bar_empty[i], 1);
             }
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < 4; ++i) {
                 umma::mbar_init(&bar_tfull[i], 1);
-                umma::mbar_init(&bar_tempty[i], kEpilogueWarps);
+                umma::mbar_init(&bar_tempty[i], kEpilogueWarps / a.teams);
+            }
+            for (int i = 0; i < 2; ++i) {
                 umma::mbar_init(&bar_rfull[i], kRareWarps);
-                umma::mbar_init(&bar_rempty[i], kEpilogueWarps);
+                umma::mbar_init(&bar_rempty[i], kEpilogueWarps / a.teams);
             }
             for (int i = 0; i < 4; ++i) {
                 umma::mbar_init(&bar_ring_full[i], 1);
@@ -719,28 +723,75 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
         const int e = warp - (kMmaWarp + 1);
         const int q = warp & 3;  // TMEM lane quarter this warp may access (warps 5..12 -> 1,2,3,0,1,2,3,0)
         const int L = q * 32 + lane;
-        const int half = e >> 2;
+        // one team: the two warps of a quarter split the columns of a tile; two teams (N <= 64, two staging tiles):
+        // warps e < 4 take the even tiles of this CTA, the others the odd ones, a thread = a whole row — two tiles
+        // in the epilogue at a time, which is what a latency-bound epilogue (pair kinds: one MMA step per tile) needs
+        const int teams = a.teams;
+        const int team = teams == 2 ? e >> 2 : 0;
+        const int half = teams == 2 ? 0 : e >> 2;
         const int tp = half * 32 + lane;  // thread of the quarter's warp pair
         const int cph = ((N / 16 + 1) / 2) * 16;  // columns of half 0 (multiple of 16)
-        const int c0 = half ? cph : 0, c1 = half ? N : cph;
+        const int c0 = teams == 2 ? 0 : (half ? cph : 0), c1 = teams == 2 ? N : (half ? N : cph);
         const bool has_rare = KIND == kKindStationary && a.rare_rs != nullptr && !(a.ablate & 2);
         const uint32_t ldr = 4u * (uint32_t)N + 16u;  // staging row pitch in bytes (+16: conflict-free thread-per-row access)
         uint8_t* const stage_gen = smem_raw + (sbase - umma::smem_u32(smem_raw)) + (size_t)S * a.stage_bytes;
         const int nrb = a.nrb;
         int overflow = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const int buf = it % nbuf, rb = it % nrb;
-            uint8_t* const Rb = stage_gen + (size_t)rb * kTM * ldr;
-            uint8_t* const myrow = Rb + (size_t)L * ldr;
-            long long row = -1;  // output row (final kinds) / pair-buffer row
+        // output row (final kinds) / pair-buffer row of this thread's lane in a tile, and its normaliser
+        auto load_row = [&](int tile, long long& row, float& nrm) {
+            row = -1;
             if (KIND == kKindStationary) {
                 const long long v = (long long)tile * kTM + L;
                 if (v < a.V) row = a.row_map ? a.row_map[v] : v;
             } else {
                 row = a.out_pos[(size_t)tile * kTM + L];
             }
-            const float nrm = (KIND != kKindPairBuf && a.norm && row >= 0) ? a.norm[row] : 0.f;
+            nrm = (KIND != kKindPairBuf && a.norm && row >= 0) ? a.norm[row] : 0.f;
+        };
+        // copy-out: every warp copies what it wrote itself — its 32 rows x its columns [c0, c0 + nv) — so the staging
+        // tile needs no cross-warp synchronisation.  16-byte chunk ch of the warp's part of a row -> offset in the
+        // staging row, destination base and pitch:
+        const int nv = KIND == kKindPairBuf ? c1 - c0 : max(0, min(c1, a.ncols) - c0);  // valid columns of this half
+        const int CW = nv >> 2;                                                       // chunks per row
+        auto copy_geometry = [&](int ch, size_t& pitch, uint32_t& soff) -> uint8_t* {
+            if (KIND == kKindPairBuf) {
+                pitch = (size_t)N * 4;
+                soff = 4 * c0 + ch * 16;
+                return reinterpret_cast<uint8_t*>(a.pair_out + c0) + ch * 16;
+            }
+            if (a.out_f) {
+                pitch = (size_t)a.out_f_pitch * 4;
+                soff = 4 * c0 + ch * 16;
+                return reinterpret_cast<uint8_t*>(a.out_f + c0) + ch * 16;
+            }
+            // split-half rows: columns c0 + 8 cc .. + 7 of plane `plane` = block cc / 2 of this half, second part of it if cc is odd
+            const int hc = CW >> 1, plane = ch >= hc ? 1 : 0, cc = ch - plane * hc;
+            pitch = (size_t)a.out_pitch * 2;
+            soff = 4 * c0 + (cc >> 1) * 64 + plane * 32 + (cc & 1) * 16;
+            return reinterpret_cast<uint8_t*>(a.out_h + (plane ? a.out_lo : a.out_hi) + c0) + cc * 16;
+        };
+        // chunks per row a power of two (the rule): this lane copies chunk lane % CW of every (32 / CW)-th row
+        int cw_shift = -1;
+        for (int sh = 0; sh <= 5; ++sh)
+            if ((1 << sh) == CW) cw_shift = sh;
+        const int co_r0 = cw_shift >= 0 ? lane >> cw_shift : 0, co_rstep = cw_shift >= 0 ? 32 >> cw_shift : 1;
+        size_t co_pitch = 0;
+        uint32_t co_src = 0;
+        uint8_t* const co_base = copy_geometry(lane & (CW - 1), co_pitch, co_src);
+        long long row_n = -1;
+        float nrm_n = 0.f;
+        const int tstep = teams * (int)gridDim.x;
+        it = team;
+        if ((int)blockIdx.x + team * (int)gridDim.x < ntiles) load_row(blockIdx.x + team * gridDim.x, row_n, nrm_n);
+        for (int tile = blockIdx.x + team * gridDim.x; tile < ntiles; tile += tstep, it += teams) {
+            const int buf = it % nbuf, rb = it % nrb;
+            uint8_t* const Rb = stage_gen + (size_t)rb * kTM * ldr;
+            uint8_t* const myrow = Rb + (size_t)L * ldr;
+            // destination row and normaliser of this tile (loaded one tile ahead), the next tile's on their way
+            const long long row = row_n;
+            const float nrm = nrm_n;
+            if (tile + tstep < ntiles) load_row(tile + tstep, row_n, nrm_n);
             // groups of this tile that hold data; importance variant: the weight of every dense slot's row
             const int used = a.by_slot ? steps_per_tile : min(G, steps_per_tile * a.chunks);
             float wgt[8];
@@ -761,8 +812,7 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
             umma::mbar_wait(&bar_tfull[buf], (it / nbuf) & 1);
             umma::tc_fence_after();
             const uint32_t t_acc = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * accw);
-#pragma unroll
-            for (int cb = 0; cb < 4; ++cb) {
+            for (int cb = 0; cb < 8; ++cb) {
                 const int n0 = c0 + 16 * cb;
                 if (n0 >= c1) break;  // warp-uniform
                 float v[16];
@@ -772,11 +822,13 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
                     if (g < used) {
-                        float m[16], c[16];
-                        umma::tmem_ld16(t_acc + g * 2 * N + n0, m);
-                        umma::tmem_ld16(t_acc + g * 2 * N + N + n0, c);
+                        uint32_t mc[32];  // main and correction columns: both loads in flight, one wait
+                        umma::tmem_ld16_issue(t_acc + g * 2 * N + n0, *reinterpret_cast<uint32_t(*)[16]>(&mc[0]));
+                        umma::tmem_ld16_issue(t_acc + g * 2 * N + N + n0, *reinterpret_cast<uint32_t(*)[16]>(&mc[16]));
+                        umma::tmem_ld_wait32(mc);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = fmaf(m[j] + c[j], wgt[g], v[j]);
+                        for (int j = 0; j < 16; ++j)
+                            v[j] = fmaf(__uint_as_float(mc[j]) + __uint_as_float(mc[16 + j]), wgt[g], v[j]);
                     }
                 }
 #pragma unroll
@@ -835,31 +887,29 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
             umma::tc_fence_before();
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(&bar_tempty[buf]);
-            if (half == 0) s_dst[L] = (a.ablate & 8) ? -1 : (int)row;
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-            // copy-out of rows q * 32 .. q * 32 + 31: chunk = 16 bytes, consecutive threads = consecutive chunks of a row
-            {
-                const int CH = (KIND == kKindPairBuf ? N : a.ncols) >> 2;  // chunks per row
-                const int hc = CH >> 1;                                   // per plane of the split-half format
-                for (int idx = tp; idx < 32 * CH; idx += 64) {
-                    const int r = idx / CH, ch = idx - r * CH;
-                    const int drow = s_dst[q * 32 + r];
-                    if (drow < 0) continue;
-                    const uint8_t* src = Rb + (size_t)(q * 32 + r) * ldr;
-                    uint8_t* dst;
-                    if (KIND == kKindPairBuf) {
-                        dst = reinterpret_cast<uint8_t*>(a.pair_out + (size_t)drow * N) + ch * 16;
-                        src += ch * 16;
-                    } else if (a.out_f) {
-                        dst = reinterpret_cast<uint8_t*>(a.out_f + (size_t)drow * a.out_f_pitch) + ch * 16;
-                        src += ch * 16;
-                    } else {
-                        // columns 8 cc .. 8 cc + 7 of plane `plane`: block cc / 2 of the row, second half of it if cc is odd
-                        const int plane = ch >= hc ? 1 : 0, cc = ch - plane * hc;
-                        dst = reinterpret_cast<uint8_t*>(a.out_h + (size_t)drow * a.out_pitch + (plane ? a.out_lo : a.out_hi)) + cc * 16;
-                        src += (cc >> 1) * 64 + plane * 32 + (cc & 1) * 16;
+            __syncwarp();
+            // copy-out: consecutive lanes = consecutive 16-byte chunks of a row
+            const int myrow_dst = (a.ablate & 8) ? -1 : (int)row;
+            if (cw_shift >= 0) {
+#pragma unroll 4
+                for (int r = co_r0; r < 32; r += co_rstep) {
+                    const int drow = __shfl_sync(0xffffffffu, myrow_dst, r);
+                    if (drow >= 0)
+                        *reinterpret_cast<uint4*>(co_base + (size_t)drow * co_pitch) =
+                                *reinterpret_cast<const uint4*>(Rb + (size_t)(q * 32 + r) * ldr + co_src);
+                }
+            } else if (CW > 0) {  // chunks per row not a power of two
+                for (int i0 = 0; i0 < 32 * CW; i0 += 32) {
+                    const int idx = i0 + lane;
+                    const int r = min(idx / CW, 31);
+                    const int drow = __shfl_sync(0xffffffffu, myrow_dst, r);
+                    if (idx < 32 * CW && drow >= 0) {
+                        size_t pitch;
+                        uint32_t soff;
+                        uint8_t* const base = copy_geometry(idx - r * CW, pitch, soff);
+                        *reinterpret_cast<uint4*>(base + (size_t)drow * pitch) =
+                                *reinterpret_cast<const uint4*>(Rb + (size_t)(q * 32 + r) * ldr + soff);
                     }
-                    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
                 }
             }
             if (has_rare) {
@@ -919,7 +969,7 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
             const int rw = warp - kRareWarp0;
             const int rt = rw * 32 + lane;  // thread of the four rare warps
             const int LP = a.rare_lp;
-            const int NG = kTM / LP;            // lane groups; group g owns rows g, g + NG, g + 2 NG, ... so that the
+            const int NG = kRareWarps * 32 / LP;  // lane groups; group g owns rows g, g + NG, g + 2 NG, ... so that the
             const int g = rt / LP;              // pairs of one ring chunk (consecutive rows) spread over all groups
             const int lig = lane & (LP - 1);
             const bool colok = 4 * lig < N;
@@ -935,53 +985,66 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                 uint8_t* const Rb = stage_gen + (size_t)rb * kTM * ldr;
                 const long long t0 = (long long)tile * kTM;
                 long long* const rs = s_rs[it & 1];  // rare-segment bounds of the tile's rows (double-buffered: one barrier per tile)
-                rs[rt] = a.rare_rs[min(t0 + rt, (long long)a.V)];
-                if (rt == 0) rs[kTM] = a.rare_rs[min(t0 + kTM, (long long)a.V)];
-                asm volatile("bar.sync 5, 128;" ::: "memory");
-                const long long tp0 = rs[0], tp1 = rs[kTM];
+                if (rt <= kTM) rs[rt] = a.rare_rs[min(t0 + rt, (long long)a.V)];
+                asm volatile("bar.sync 5, %0;" ::"n"(kRareWarps * 32) : "memory");
+                const long long tp0 = rs[0];
+                const int total = (int)(rs[kTM] - tp0);  // pairs of the tile; all positions below are relative to tp0
+                float wnext = (a.imp && lane < total) ? a.imp[a.rare_in[tp0 + lane]] : 0.f;  // first chunk's importances
                 umma::mbar_wait(&bar_rempty[rb], ((it / nrb) & 1) ^ 1);
                 int cr = g;  // current row
-                long long p = rs[cr], pe = rs[cr + 1];
+                int p = (int)(rs[cr] - tp0), pe = (int)(rs[cr + 1] - tp0);
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                uint8_t* dst = Rb + (size_t)cr * ldr + 16 * lig;
+                const uint32_t dstep = (uint32_t)NG * ldr;
                 auto finish_row = [&]() {
-                    if (colok) *reinterpret_cast<float4*>(Rb + (size_t)cr * ldr + 16 * lig) = acc;
+                    if (colok) *reinterpret_cast<float4*>(dst) = acc;
                     acc = make_float4(0.f, 0.f, 0.f, 0.f);
                     cr += NG;
+                    dst += dstep;
                     if (cr < kTM) {
-                        p = rs[cr];
-                        pe = rs[cr + 1];
+                        p = (int)(rs[cr] - tp0);
+                        pe = (int)(rs[cr + 1] - tp0);
                     }
                 };
-                for (long long c = tp0; c < tp1; c += CP) {
-                    const long long ce = min(c + CP, tp1);
-                    if (a.imp) {  // importance of the chunk's pairs (one per lane; CP <= 32), fetched while the chunk lands
+                for (int cb = 0; cb < total; cb += CP) {
+                    const int ce = min(cb + CP, total);
+                    if (a.imp) {  // importance of the chunk's pairs (one per lane; CP <= 32), loaded one chunk ahead
                         __syncwarp();
-                        s_w[rw][lane] = c + lane < ce ? a.imp[a.rare_in[c + lane]] : 0.f;
+                        s_w[rw][lane] = wnext;
                         __syncwarp();
+                        wnext = ce + lane < total ? a.imp[a.rare_in[tp0 + ce + lane]] : 0.f;
                     }
                     umma::mbar_wait(&bar_ring_full[rsl], rph);
-                    const float* const chunk = ring + (size_t)rsl * CP * N;
+                    const float* const chunk = ring + (size_t)rsl * CP * N + (colok ? 4 * lig : 0);
                     while (cr < kTM && p < ce) {
-                        const long long hi = min(pe, ce);
-                        while (p < hi) {
-                            float4 t[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                t[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (p + u < hi && colok)
-                                    t[u] = *reinterpret_cast<const float4*>(chunk + (size_t)(p + u - c) * N + 4 * lig);
+                        const int hi = min(pe, ce);
+                        const float* src = chunk + (p - cb) * N;
+                        if (a.imp) {
+                            for (; p < hi; ++p, src += N) {
+                                const float4 t = *reinterpret_cast<const float4*>(src);
+                                const float w = s_w[rw][p - cb];
+                                acc.x = fmaf(t.x, w, acc.x);
+                                acc.y = fmaf(t.y, w, acc.y);
+                                acc.z = fmaf(t.z, w, acc.z);
+                                acc.w = fmaf(t.w, w, acc.w);
                             }
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                if (p + u < hi) {
-                                    const float w = a.imp ? s_w[rw][p + u - c] : 1.f;
-                                    acc.x = fmaf(t[u].x, w, acc.x);
-                                    acc.y = fmaf(t[u].y, w, acc.y);
-                                    acc.z = fmaf(t[u].z, w, acc.z);
-                                    acc.w = fmaf(t[u].w, w, acc.w);
-                                }
+                        } else {
+                            for (; p + 1 < hi; p += 2, src += 2 * N) {  // both loads in flight, added in pair order
+                                const float4 t = *reinterpret_cast<const float4*>(src);
+                                const float4 u = *reinterpret_cast<const float4*>(src + N);
+                                acc.x = (acc.x + t.x) + u.x;
+                                acc.y = (acc.y + t.y) + u.y;
+                                acc.z = (acc.z + t.z) + u.z;
+                                acc.w = (acc.w + t.w) + u.w;
                             }
-                            p = min(p + 4, hi);
+                            if (p < hi) {
+                                const float4 t = *reinterpret_cast<const float4*>(src);
+                                acc.x += t.x;
+                                acc.y += t.y;
+                                acc.z += t.z;
+                                acc.w += t.w;
+                                ++p;
+                            }
                         }
                         if (p < pe) break;  // the row continues in the next chunk
                         finish_row();
@@ -1098,8 +1161,16 @@ void conv(const Plan& P, const ConvArgs& c, cudaStream_t s) {
     // two TMEM buffers whenever [main N | corr N] fits twice (the epilogue of a tile then overlaps the next tile's
     // MMAs; for N = 128 that leaves one accumulator group); dev knob gx_single_tmem: round-2a policy (N > 64: one
     // buffer, two groups)
-    k.nbuf = (g_single_tmem && N > 64) ? 1 : (2 * N * 2 <= 512 ? 2 : 1);
-    k.G = std::max(1, std::min(g_acc_groups > 0 ? g_acc_groups : 4, 512 / (2 * N * k.nbuf)));
+    // accumulator groups as before (stationary: 4 / 4 / 2 / 1 for N = 16 / 32 / 64 / 128; a pair tile has only
+    // `chunks` MMA steps), then as many TMEM buffers as fit (<= 4): a buffer is held from the tile's first MMA to
+    // the end of its TMEM loads, so more buffers = deeper MMA / epilogue overlap
+    k.G = g_acc_groups > 0 ? g_acc_groups : std::max(1, std::min(4, 256 / (2 * N)));
+    k.G = std::max(1, std::min(k.G, 512 / (2 * N)));
+    k.nbuf = std::max(1, std::min(4, 512 / (2 * N * k.G)));
+    if (g_single_tmem && N > 64) {
+        k.nbuf = 1;
+        k.G = std::max(1, std::min(g_acc_groups > 0 ? g_acc_groups : 4, 512 / (2 * N)));
+    }
     k.rare_lp = 4;
     while (k.rare_lp * 4 < N) k.rare_lp <<= 1;
     k.zero_row = (int)P.V_in;
@@ -1116,6 +1187,7 @@ void conv(const Plan& P, const ConvArgs& c, cudaStream_t s) {
     k.stages = (int)std::max<size_t>(2, std::min<size_t>(8, (budget - ring_bytes - k.nrb * stage_tile) / k.stage_bytes));
     if (g_max_stages > 0) k.stages = std::max(2, std::min(k.stages, g_max_stages));
     const size_t smem = (size_t)k.stages * k.stage_bytes + k.nrb * stage_tile + ring_bytes + 1024;
+    k.teams = (!g_one_team && N <= 64 && k.nrb == 2 && k.nbuf >= 2) ? 2 : 1;
     ASRB_REQUIRE(smem <= 227 * 1024 - 4096, "gx conv: shared-memory budget exceeded");  // 4 KB static (barriers, row bounds)
     k.wscale = ldexpf(1.f, -c.scale_exp);
     k.ncols = c.ncols;
@@ -1150,6 +1222,10 @@ void conv(const Plan& P, const ConvArgs& c, cudaStream_t s) {
 
     if (has_rare) {
         KArgs r = k;
+        if (k.chunks == 1) {  // a pair tile is one MMA step: one accumulator group (no change of the result), more buffers
+            r.G = 1;
+            r.nbuf = std::max(1, std::min(4, 512 / (2 * N)));
+        }
         r.gidx = P.pt_gidx.get();
         r.tile_slot = P.pt_slot.get();
         r.out_pos = P.pt_out.get();

@@ -89,6 +89,7 @@ void set_tma_gather(int v);
 void set_l1_gather(int v);
 void set_max_stages(int v);
 void set_single_tmem(int v);
+void set_one_team(int v);
 void set_ablate(int v);  // timing experiments only
 void conv(const Plan& P, const ConvArgs& a, cudaStream_t s);
 

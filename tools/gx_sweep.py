@@ -29,7 +29,7 @@ def timeit(fn, reps=5):
     return e0.elapsed_time(e1) / reps
 
 # gx_ablate (timing only, garbage results): 1 no filter copies, 2 no pair-buffer reads, 4 no row gathers, 8 no stores, 16 no MMAs
-configs = [dict(), dict(gx_single_tmem=1), dict(gx_max_stages=2)] + [dict(gx_ablate=v) for v in (1, 2, 4, 8, 16, 10, 15, 31)]
+configs = [dict(), dict(gx_one_team=1)] + [dict(gx_ablate=v) for v in (2, 8, 16, 31)]
 for lev, cin, cout in shapes:
     plan = plans[lev]
     V = plan.num_out
@@ -40,7 +40,7 @@ for lev, cin, cout in shapes:
     sc = gx.Scratch()
     res = {}
     for cfg in configs:
-        for k in ("gx_l1_gather", "gx_max_stages", "gx_acc_groups", "gx_ablate", "gx_single_tmem"):
+        for k in ("gx_l1_gather", "gx_max_stages", "gx_acc_groups", "gx_ablate", "gx_single_tmem", "gx_one_team"):
             _lib.set_option(k, cfg.get(k, 0))
         res[json.dumps(cfg)] = round(timeit(lambda: gx.conv(plan, x, f, out=out, scratch=sc)), 3)
     print("L%d %dx%d:" % (lev, cin, cout), res, flush=True)
