@@ -65,6 +65,7 @@ SIGNATURES = {
     "asr_gx_conv": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32,
                            _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp]),
     "asr_gx_overflow": (_i32, [_vp, C.POINTER(C.c_int)]),
+    "asr_gx_trace": (_i32, [_vp, _i32, C.POINTER(C.c_uint)]),
     "asr_shard_positions": (_i32, [_vp, _i64, _vp, _vp]),
     "asr_shard_owner": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp]),
     "asr_shard_need_mask": (_i32, [_vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp]),

@@ -114,6 +114,7 @@ int asr_set_option(const char* name, int value) {
         else if (std::string(name) == "gx_ablate") gx::set_ablate(value);
         else if (std::string(name) == "gx_single_tmem") gx::set_single_tmem(value);
         else if (std::string(name) == "gx_one_team") gx::set_one_team(value);
+        else if (std::string(name) == "gx_trace") gx::set_trace(value);
         else if (std::string(name) == "tc_stages") sparse_conv_tc_tune(value, 0);
         else if (std::string(name) == "tc_row_groups") sparse_conv_tc_tune(0, value);
         else throw Error(kInvalidArgument, std::string("unknown option: ") + name);
@@ -474,6 +475,13 @@ int asr_shard_push(void* const* peer_base, int world, int rank, int64_t offset, 
     return guarded([&] {
         ASRB_REQUIRE(peer_base && seg_off, "shard_push: null argument");
         shard_push(peer_base, world, rank, offset, pitch, seg_off, nseg, seg_len, d_rows, num_rows, d_mask, S(stream));
+    });
+}
+
+int asr_gx_trace(void* stream, int ctas, unsigned* counters) {
+    return guarded([&] {
+        ASRB_REQUIRE(counters != nullptr && ctas > 0, "asr_gx_trace: null output");
+        gx::trace_read(counters, ctas, S(stream));
     });
 }
 

@@ -75,44 +75,90 @@ __device__ __forceinline__ int second_round_face(int lane) {  // lane 0..29 -> p
     return p < 31 ? (p - 7) >> 2 : p - 31;
 }
 
+// four lookups of a lane with all first probes in flight together (key 0 = no lookup)
+__device__ __forceinline__ void table_find4(const KeyTableView t, const Key (&k)[4], long long (&out)[4]) {
+    uint32_t s[4];
+    ulonglong2 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        s[j] = hash_key(k[j]) & t.mask;
+        v[j] = make_ulonglong2(kNoKey, 0);
+        if (k[j]) v[j] = __ldg(reinterpret_cast<const ulonglong2*>(t.e + s[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        out[j] = -1;
+        if (!k[j]) continue;
+        for (;;) {
+            if (v[j].x == k[j]) {
+                out[j] = (long long)v[j].y;
+                break;
+            }
+            if (v[j].x == kNoKey) break;
+            s[j] = (s[j] + 1) & t.mask;
+            v[j] = __ldg(reinterpret_cast<const ulonglong2*>(t.e + s[j]));
+        }
+    }
+}
+
 // pass 1: 55-bit slot mask per voxel; the indices found are kept, in slot order, in `stash`
-// ([V][32] int32: a row has at most 1 + 6 x 4 = 25 entries), so pass 2 is a plain copy
+// ([V][32] int32: a row has at most 1 + 6 x 4 = 25 entries), so pass 2 is a plain copy.
+// A warp owns FOUR consecutive voxels (the kernel is bound by the latency of dependent hash probes: round 2's
+// version with one voxel per warp had 6 probes in flight per warp in round 1): round 1 = the 4 x 6 same-level
+// probes at once (octet o of the warp = voxel o, lanes 1..6 of it = faces), round 2 = up to 4 x 30 probes, four
+// per lane issued together.
 __global__ void __launch_bounds__(256)
 adjacency_mask_kernel(const Key* __restrict__ keys, long long V, const KeyTableView table,
                       unsigned long long* __restrict__ mask, int32_t* __restrict__ count, int32_t* __restrict__ stash) {
     const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (w >= V) return;
-    const Cell c = key_cell(keys[w]);
-    unsigned long long m = lane == 0 ? 1ULL : 0ULL;
-    long long i1 = lane == 0 ? w : -1, i2 = -1;  // what this lane found in round 1 / round 2
-    int s1 = 0, s2 = 0;
-    if (lane >= 1 && lane < 7) {
-        const Probe pr = make_probe(c, lane);
-        if (pr.key) i1 = table_find(table, pr.key);
-        if (i1 >= 0) {
-            m = 1ULL << lane;
-            s1 = lane;
+    const long long v0 = w * 4;
+    if (v0 >= V) return;
+    const int o = lane >> 3, f = lane & 7;
+    long long i1 = -1;  // what this lane found in round 1 (lane 8 o: the voxel itself)
+    if (v0 + o < V) {
+        if (f == 0) {
+            i1 = v0 + o;
+        } else if (f < 7) {
+            const Probe pr = make_probe(key_cell(keys[v0 + o]), f);
+            if (pr.key) i1 = table_find(table, pr.key);
         }
     }
-    const unsigned same_faces = __ballot_sync(0xffffffffu, lane >= 1 && lane < 7 && i1 >= 0) >> 1;  // bit f: face f has a same-level neighbour
-    if (lane < 30 && !((same_faces >> second_round_face(lane)) & 1)) {
-        const Probe pr = make_probe(c, lane + 7);
-        if (pr.key) i2 = table_find(table, pr.key);
-        if (i2 >= 0) {
-            m |= 1ULL << pr.slot;
-            s2 = pr.slot;
+    const unsigned found1 = __ballot_sync(0xffffffffu, i1 >= 0);  // bit 8 o + f
+    Key k2[4];
+    int s2[4];
+    long long i2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        k2[j] = 0;
+        s2[j] = 0;
+        if (v0 + j < V && lane < 30) {
+            const unsigned same_faces = (found1 >> (8 * j + 1)) & 0x3fu;  // bit f - 1: face f has a same-level neighbour
+            if (!((same_faces >> second_round_face(lane)) & 1)) {
+                const Probe pr = make_probe(key_cell(keys[v0 + j]), lane + 7);
+                k2[j] = pr.key;
+                s2[j] = pr.slot;
+            }
         }
     }
-    const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)m);
-    const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(m >> 32));
-    m = ((unsigned long long)hi << 32) | lo;
-    int32_t* row = stash + w * 32;
-    if (i1 >= 0) row[__popcll(m & ((1ULL << s1) - 1))] = (int32_t)i1;
-    if (i2 >= 0) row[__popcll(m & ((1ULL << s2) - 1))] = (int32_t)i2;
-    if (lane == 0) {
-        mask[w] = m;
-        count[w] = __popcll(m);
+    table_find4(table, k2, i2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (v0 + j >= V) break;  // warp-uniform
+        unsigned long long m = 0;
+        const bool mine1 = o == j && i1 >= 0;
+        if (mine1) m |= 1ULL << f;
+        if (i2[j] >= 0) m |= 1ULL << s2[j];
+        const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)m);
+        const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(m >> 32));
+        m = ((unsigned long long)hi << 32) | lo;
+        int32_t* row = stash + (v0 + j) * 32;
+        if (mine1) row[__popcll(m & ((1ULL << f) - 1))] = (int32_t)i1;
+        if (i2[j] >= 0) row[__popcll(m & ((1ULL << s2[j]) - 1))] = (int32_t)i2[j];
+        if (lane == 0) {
+            mask[v0 + j] = m;
+            count[v0 + j] = __popcll(m);
+        }
     }
 }
 
@@ -199,7 +245,7 @@ static void build_adjacency(GridLevel& g, const KeyTable& table, cudaStream_t s)
     DevBuf<int32_t> stash((size_t)V * 32, s);
     if (V) {
         ProfileScope prof("adjacency_mask", s);
-        adjacency_mask_kernel<<<grid_for((size_t)V * 32, 256), 256, 0, s>>>(g.keys.get(), V, table.view(), mask.get(),
+        adjacency_mask_kernel<<<grid_for((size_t)((V + 3) / 4) * 32, 256), 256, 0, s>>>(g.keys.get(), V, table.view(), mask.get(),
                                                                             count.get(), stash.get());
         ASRB_CHECK_LAUNCH();
     }

@@ -353,6 +353,101 @@ ball_query_kernel(const KeyTableView cells, const float4* __restrict__ spts, Bin
     }
 }
 
+// ---- rows of more than kStash hits (1.2 % of the rows, 8 % of the pairs on the bench cloud, up to ~1100 hits) ----
+// A warp per such row (the first version) streamed the row's candidates with 32 lanes and rank-sorted n keys in
+// n^2 / 32 steps through global memory: 3.2 ms for 42 k rows.  Now: the rows are listed, a BLOCK takes a row:
+// 256 lanes stream the windows, hits are appended to shared memory (any order: the keys (d2, index) are
+// distinct, the rank sort fixes the result), and the rank of each key is counted against the shared copy.
+constexpr int kHeavyKeys = 2048;  // keys of a row kept in shared memory; beyond that they go through `gkeys`
+
+__global__ void __launch_bounds__(256)
+heavy_list_kernel(const int64_t* __restrict__ splits, long long nq, int32_t* __restrict__ list, int* __restrict__ count) {
+    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    if (splits[q + 1] - splits[q] > kStash) list[atomicAdd(count, 1)] = (int32_t)q;
+}
+
+__global__ void __launch_bounds__(256)
+ball_query_heavy_kernel(const KeyTableView cells, const float4* __restrict__ spts, BinFrame f,
+                        const float* __restrict__ queries, const float* __restrict__ radii,
+                        const int64_t* __restrict__ splits, const int32_t* __restrict__ list,
+                        const int* __restrict__ count, unsigned long long* __restrict__ gkeys,
+                        int32_t* __restrict__ out_idx, float* __restrict__ out_d2) {
+    __shared__ unsigned long long s_key[kHeavyKeys];
+    __shared__ unsigned s_begin[32];
+    __shared__ int s_pre[33];
+    __shared__ int s_n;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int nheavy = *count;
+    for (int h = blockIdx.x; h < nheavy; h += gridDim.x) {
+        const long long q = list[h];
+        const float qx = queries[3 * q], qy = queries[3 * q + 1], qz = queries[3 * q + 2];
+        const float r = radii[q];
+        const float r2 = __fmul_rn(r, r);
+        const int64_t out_base = splits[q];
+        const int row_n = (int)(splits[q + 1] - out_base);
+        __syncthreads();  // the previous row's shared data is no longer read
+        if (tid < 32) {
+            int len = 0;
+            unsigned begin = 0;
+            int lo[3], hi[3];
+            const float qq[3] = {qx, qy, qz};
+            const int sh = query_box(qq, r, f, lo, hi);
+            if (lane < 27) {
+                const int cx = (lo[0] >> sh) + lane % 3, cy = (lo[1] >> sh) + (lane / 3) % 3, cz = (lo[2] >> sh) + lane / 9;
+                if (cx <= (hi[0] >> sh) && cy <= (hi[1] >> sh) && cz <= (hi[2] >> sh)) {
+                    const Key k = morton3(cx, cy, cz) | (Key(1) << (3 * (kGridBits - sh)));
+                    const long long v = table_find(cells, k);
+                    if (v >= 0) {
+                        begin = (unsigned)v;
+                        len = (int)((unsigned long long)v >> 32) - (int)begin;
+                    }
+                }
+            }
+            int pre = len;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, pre, d);
+                if (lane >= d) pre += v;
+            }
+            s_begin[lane] = begin;
+            s_pre[lane + 1] = pre;
+            if (lane == 0) {
+                s_pre[0] = 0;
+                s_n = 0;
+            }
+        }
+        __syncthreads();
+        const int total = s_pre[32];
+        for (int t = tid; t < total; t += 256) {
+            int c = 0;  // last cell with s_pre[c] <= t
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+                if (c + step < 32 && s_pre[c + step] <= t) c += step;
+            const float4 p = __ldg(spts + s_begin[c] + (unsigned)(t - s_pre[c]));
+            const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            if (d2 < r2) {
+                const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | __float_as_uint(p.w);
+                const int pos = atomicAdd(&s_n, 1);
+                if (pos < kHeavyKeys) s_key[pos] = key;
+                else gkeys[out_base + pos] = key;
+            }
+        }
+        __threadfence_block();
+        __syncthreads();
+        const int ns = min(row_n, kHeavyKeys);
+        for (int i = tid; i < row_n; i += 256) {
+            const unsigned long long mine = i < kHeavyKeys ? s_key[i] : gkeys[out_base + i];
+            int rank = 0;
+            for (int j = 0; j < ns; ++j) rank += s_key[j] < mine ? 1 : 0;
+            for (int j = kHeavyKeys; j < row_n; ++j) rank += gkeys[out_base + j] < mine ? 1 : 0;
+            out_idx[out_base + rank] = (int32_t)(unsigned)mine;
+            out_d2[out_base + rank] = __uint_as_float((unsigned)(mine >> 32));
+        }
+    }
+}
+
 // compat = (min(s_v, 2 r_p) / max(s_v, 2 r_p))^2   (nsearch.cpp:149-161)
 __global__ void __launch_bounds__(256)
 scale_compat_kernel(const float* __restrict__ sizes, const float* __restrict__ radii, const int32_t* __restrict__ idx,
@@ -470,13 +565,24 @@ void search_fill(Search& S, int32_t* d_idx, float* d_d2, int64_t* d_splits, cuda
     DevBuf<unsigned long long> keys((size_t)S.num_pairs, s);
     ProfileScope prof("ball_query_fill_sort", s);
     if (S.stash.size()) {
+        // rows of <= kStash hits straight from the stash, the longer ones by a block each
         stash_rows_kernel<<<grid_for((size_t)S.nq * 32, 256), 256, 0, s>>>(S.stash.get(), S.splits.get(), S.nq, d_idx, d_d2);
         ASRB_CHECK_LAUNCH();
+        DevBuf<int32_t> list((size_t)S.nq, s);
+        DevBuf<int> count(1, s);
+        ASRB_CUDA(cudaMemsetAsync(count.get(), 0, sizeof(int), s));
+        heavy_list_kernel<<<grid_for((size_t)S.nq, 256), 256, 0, s>>>(S.splits.get(), S.nq, list.get(), count.get());
+        ASRB_CHECK_LAUNCH();
+        const unsigned blocks = (unsigned)std::min<size_t>((size_t)S.nq, 148 * 8);
+        ball_query_heavy_kernel<<<blocks, 256, 0, s>>>(S.cells.view(), (const float4*)S.spts.get(), f, S.queries, S.radii,
+                                                       S.splits.get(), list.get(), count.get(), keys.get(), d_idx, d_d2);
+        ASRB_CHECK_LAUNCH();
+    } else {
+        ball_query_kernel<true><<<grid_for(S.nq, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
+                S.cells.view(), (const float4*)S.spts.get(), f, S.queries, S.radii, S.nq, nullptr, S.splits.get(), keys.get(),
+                d_idx, d_d2, nullptr);
+        ASRB_CHECK_LAUNCH();
     }
-    ball_query_kernel<true><<<grid_for(S.nq, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
-            S.cells.view(), (const float4*)S.spts.get(), f, S.queries, S.radii, S.nq, nullptr, S.splits.get(), keys.get(),
-            d_idx, d_d2, S.stash.size() ? S.stash.get() : nullptr);
-    ASRB_CHECK_LAUNCH();
     S.stash.release();
 }
 

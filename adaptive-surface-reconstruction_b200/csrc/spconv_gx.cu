@@ -7,10 +7,10 @@
 //
 //  * Activations live in HBM in a split-half format between layers: x = hi + lo with two fp16 planes per
 //    row (same 4 bytes per element as fp32; |x| < 65504, 22+ significant bits for |x| >= 2^-3, absolute
-//    error <= 2^-25 below).  Gathered rows are then tensor-core operands AS THEY LIE in memory: the TMA
-//    engine gathers them (cp.async.bulk.tensor ... tile::gather4, 4 rows x 128 bytes per instruction,
-//    128-byte swizzle) straight into the K-major operand tile — no LSU traffic, no register staging, no
-//    conversion pass, no generic->async proxy fence.
+//    error <= 2^-25 below).  Gathered rows are tensor-core operands AS THEY LIE in memory: 16-byte cp.async
+//    copies place them in the K-major 128-byte-swizzled operand tile (no register staging, no conversion).
+//    (TMA tile::gather4 does the same with one instruction per 4 rows but is instruction-rate bound on
+//    B200 — kept behind the gx_tma_gather option.)
 //  * fp32-accurate product on the fp16 pipe (2x the tf32 rate, half the operand bytes of 3xTF32):
 //    D += A_hi B_hi + A_lo B_hi + A_hi B_lo; hi*hi products are exact in fp32, the dropped lo*lo term is
 //    2^-22 relative.  Filters are packed once per bank as fp16 hi / lo of W * 2^e in the kernel's shared-
@@ -23,10 +23,16 @@
 //  * The RARE slots (finer / coarser neighbours at level transitions: 27 % of the entries spread over 48
 //    slots, present in 87 % of the rows but never dense in any row tile, measured on the bench cloud) run
 //    pair-major: entries sorted by (32768-row block, slot) fill 128-pair tiles; their products go to a
-//    compact pair buffer in ROW order, which the output-stationary epilogue of the owning row reads back
-//    as one contiguous segment (plain stores and loads, no reductions in L2).
-//  * One persistent warp-specialised kernel (TMA warp / MMA thread / 4 epilogue warps), TMEM double
-//    buffered so the epilogue of tile i overlaps the MMAs of tile i + 1.
+//    compact pair buffer in ROW order.  In the output-stationary pass a tile's piece of that buffer is
+//    contiguous: one thread streams it through a shared-memory ring with bulk copies and six warps add it
+//    up per row, in pair order, into a shared-memory staging tile.
+//  * All global traffic of the epilogue is coalesced through that staging tile (rare sums in, the rows'
+//    final memory image out, whole 128-byte lines per warp instruction): a thread-per-row epilogue costs
+//    32 LSU line transactions per warp instruction and bounded the first version of this kernel
+//    (profiles/r2_gx_ablation.txt).
+//  * One persistent warp-specialised kernel: 4 gather warps / MMA thread / ring thread / 6 rare-sum
+//    warps / 8 epilogue warps (two teams on alternate tiles when N <= 64), 2-8 operand stages, 2-4 TMEM
+//    accumulator buffers so the epilogue of a tile overlaps the MMAs of the next ones.
 #include <cuda.h>
 
 #include <mutex>
@@ -50,9 +56,11 @@ void set_max_stages(int v) { g_max_stages = v; }
 static int g_acc_groups = 0;  // dev knob: main-accumulator groups per TMEM buffer (0 = as many as fit, <= 4)
 void set_acc_groups(int g) { g_acc_groups = g; }
 // dev knob for ABLATION TIMINGS ONLY (results become garbage): bit 0 no filter copies, 1 no pair-buffer reads,
-// 2 no row gathers, 3 no output stores, 4 no MMAs
+// 2 no row gathers, 3 no output stores, 4 no MMAs, 5 no generic->async proxy fence before the MMAs
 static int g_ablate = 0;
 void set_ablate(int v) { g_ablate = v; }
+static int g_trace_on = 0;     // dev knob: per-role wait cycles into g_trace (see the kernel)
+void set_trace(int v) { g_trace_on = v; }  // 1: the stationary launch, 2: the pair-major launch
 static int g_one_team = 0;     // dev knob: one epilogue team even where two fit
 void set_one_team(int v) { g_one_team = v != 0; }
 static int g_single_tmem = 0;  // dev knob: one TMEM buffer with two accumulator groups for N > 64
@@ -70,6 +78,34 @@ constexpr int kThreads = (kRingWarp + 1) * 32;
 constexpr uint32_t kATile = kTM * 128;  // 128 rows x 128 bytes
 
 __device__ int g_overflow_flag = 0;
+
+// dev option gx_trace: cycles that one thread of every role spends in its waits, per CTA (kTraceSlots counters):
+//  0 kernel  1 gather warp 0: empty  2 MMA: full  3 MMA: tmem empty  4 epilogue warp 0: rare sums ready  5 tmem full
+//  6 its column loop  7 its copy-out  8 its whole tile loop  9 rare warp 0: staging free  10 ring chunk ready
+//  11 its whole tile loop  12 ring thread: slot free  13 epilogue warp 4: tmem full  14 MMA whole loop  15 gather warp 0 whole loop
+constexpr int kTraceSlots = 16;
+__device__ unsigned g_trace[256 * kTraceSlots];
+#ifdef GX_TRACE  // `make TRACE=1`: the instrumented build (costs ~20 % even when the option is off)
+#define GX_CLOCK() ((unsigned)clock64())
+#define GX_TRACING (a.trace != 0)
+#define GX_TIMED(cond, slot, stmt)                     \
+    do {                                               \
+        if (a.trace && (cond)) {                       \
+            const unsigned _t0 = (unsigned)clock64();  \
+            stmt;                                      \
+            tr[slot] += (unsigned)clock64() - _t0;     \
+        } else {                                       \
+            stmt;                                      \
+        }                                              \
+    } while (0)
+#else
+#define GX_CLOCK() 0u
+#define GX_TRACING false
+#define GX_TIMED(cond, slot, stmt) \
+    do {                           \
+        stmt;                      \
+    } while (0)
+#endif
 
 // ------------------------------------------------------------------------------------------ plan
 // rare entries (slot >= D) per row
@@ -408,7 +444,7 @@ struct KArgs {
     const __half* x;
     int x_pitch;
     int a_hi, a_lo, chunks;
-    int tma_gather, l1_gather, ablate;
+    int tma_gather, l1_gather, ablate, trace;
     // filters
     const uint8_t* wp;
     unsigned long long slot_bytes;
@@ -511,6 +547,10 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
     umma::tc_fence_after();
     const uint32_t tmem = tmem_slot;
     const int steps_per_tile = KIND == kKindStationary ? a.D : 1;
+    unsigned tr[kTraceSlots];
+#pragma unroll
+    for (int i = 0; i < kTraceSlots; ++i) tr[i] = 0;
+    const unsigned t_kernel0 = GX_CLOCK();
 
     if (warp < kProducerWarps) {
         // ------------------------------------------------------------------ gather producers
@@ -597,7 +637,7 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                     dst[i] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((cj ^ r) & 7) << 4));
                 }
                 for (int c = 0; c < a.chunks; ++c) {
-                    umma::mbar_wait(&bar_empty[st], ph ^ 1);
+                    GX_TIMED(warp == 0 && lane == 0, 1, umma::mbar_wait(&bar_empty[st], ph ^ 1));
                     const uint32_t stage = sbase + (uint32_t)st * a.stage_bytes;
                     if (warp == 0 && lane == 0 && (a.ablate & 1)) {
                         umma::mbar_arrive(&bar_full[st]);
@@ -645,17 +685,17 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
             int st = 0, ph = 0, it = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
                 const int buf = it % nbuf;
-                umma::mbar_wait(&bar_tempty[buf], ((it / nbuf) & 1) ^ 1);
+                GX_TIMED(true, 3, umma::mbar_wait(&bar_tempty[buf], ((it / nbuf) & 1) ^ 1));
                 umma::tc_fence_after();
                 const uint32_t acc0 = tmem + (uint32_t)(buf * accw);
                 uint32_t started = 0;  // bit g: group g's accumulators hold this tile's data (else the MMA overwrites)
                 int sc = 0;
                 for (int sidx = 0; sidx < steps_per_tile; ++sidx) {
                     for (int c = 0; c < a.chunks; ++c, ++sc) {
-                        umma::mbar_wait(&bar_full[st], ph);
+                        GX_TIMED(true, 2, umma::mbar_wait(&bar_full[st], ph));
                         // the cp.async writes (generic proxy, acquired through the barrier) -> visible to the MMA's
                         // operand reads (async proxy); this thread has no loads of its own in flight, so it is cheap
-                        umma::fence_proxy_async();
+                        if (!(a.ablate & 32)) umma::fence_proxy_async();
                         umma::tc_fence_after();
                         const uint32_t stage = sbase + (uint32_t)st * a.stage_bytes;
                         const int g = a.by_slot ? sidx : (sc % G);
@@ -808,8 +848,9 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
             }
             // the sums of the rows' rare entries are in the staging tile (columns [c0, c1) of a row are touched by
             // this thread only: they are read block by block below and replaced by the block's results)
-            if (has_rare) umma::mbar_wait(&bar_rfull[rb], (it / nrb) & 1);
-            umma::mbar_wait(&bar_tfull[buf], (it / nbuf) & 1);
+            if (has_rare) GX_TIMED(e == 0 && lane == 0, 4, umma::mbar_wait(&bar_rfull[rb], (it / nrb) & 1));
+            GX_TIMED((e == 0 || e == 4) && lane == 0, e == 0 ? 5 : 13, umma::mbar_wait(&bar_tfull[buf], (it / nbuf) & 1));
+            const unsigned t_cb0 = GX_CLOCK();
             umma::tc_fence_after();
             const uint32_t t_acc = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * accw);
             for (int cb = 0; cb < 8; ++cb) {
@@ -888,6 +929,8 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(&bar_tempty[buf]);
             __syncwarp();
+            const unsigned t_co0 = GX_CLOCK();
+            if (GX_TRACING && e == 0 && lane == 0) tr[6] += t_co0 - t_cb0;
             // copy-out: consecutive lanes = consecutive 16-byte chunks of a row
             const int myrow_dst = (a.ablate & 8) ? -1 : (int)row;
             if (cw_shift >= 0) {
@@ -912,11 +955,13 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                     }
                 }
             }
+            if (GX_TRACING && e == 0 && lane == 0) tr[7] += GX_CLOCK() - t_co0;
             if (has_rare) {
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(&bar_rempty[rb]);
             }
         }
+        if (GX_TRACING && e == 0 && lane == 0) tr[8] = GX_CLOCK() - t_kernel0;
         if (overflow) atomicOr(&g_overflow_flag, 1);
     } else if (warp == kRingWarp) {
         // ------------------------------------------------------------------ pair-buffer ring producer (one thread of
@@ -943,7 +988,7 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                 }
                 for (long long c = tp0; c < tp1; c += CP) {
                     const uint32_t bytes = (uint32_t)min((long long)CP, tp1 - c) * (uint32_t)N * 4u;
-                    umma::mbar_wait(&bar_ring_empty[rsl], rph ^ 1);
+                    GX_TIMED(true, 12, umma::mbar_wait(&bar_ring_empty[rsl], rph ^ 1));
                     umma::mbar_arrive_expect_tx(&bar_ring_full[rsl], bytes);
                     asm volatile(
                             "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ring + (uint32_t)rsl * slot_bytes),
@@ -990,7 +1035,7 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                 const long long tp0 = rs[0];
                 const int total = (int)(rs[kTM] - tp0);  // pairs of the tile; all positions below are relative to tp0
                 float wnext = (a.imp && lane < total) ? a.imp[a.rare_in[tp0 + lane]] : 0.f;  // first chunk's importances
-                umma::mbar_wait(&bar_rempty[rb], ((it / nrb) & 1) ^ 1);
+                GX_TIMED(rw == 0 && lane == 0, 9, umma::mbar_wait(&bar_rempty[rb], ((it / nrb) & 1) ^ 1));
                 int cr = g;  // current row
                 int p = (int)(rs[cr] - tp0), pe = (int)(rs[cr + 1] - tp0);
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1014,7 +1059,7 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                         __syncwarp();
                         wnext = ce + lane < total ? a.imp[a.rare_in[tp0 + ce + lane]] : 0.f;
                     }
-                    umma::mbar_wait(&bar_ring_full[rsl], rph);
+                    GX_TIMED(rw == 0 && lane == 0, 10, umma::mbar_wait(&bar_ring_full[rsl], rph));
                     const float* const chunk = ring + (size_t)rsl * CP * N + (colok ? 4 * lig : 0);
                     while (cr < kTM && p < ce) {
                         const int hi = min(pe, ce);
@@ -1061,6 +1106,17 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                 if (lane == 0) umma::mbar_arrive(&bar_rfull[rb]);
             }
         }
+    }
+    if (GX_TRACING && lane == 0) {
+        // every role's lane 0 holds its own counters; slot ownership is disjoint
+        const unsigned now = GX_CLOCK() - t_kernel0;
+        unsigned* out = g_trace + (blockIdx.x & 255) * kTraceSlots;
+        if (warp == 0) { out[0] = now; out[1] = tr[1]; out[15] = now; }
+        if (warp == kMmaWarp) { out[2] = tr[2]; out[3] = tr[3]; out[14] = now; }
+        if (warp == kMmaWarp + 1) { out[4] = tr[4]; out[5] = tr[5]; out[6] = tr[6]; out[7] = tr[7]; out[8] = tr[8]; }
+        if (warp == kMmaWarp + 5) out[13] = tr[13];
+        if (warp == kRareWarp0) { out[9] = tr[9]; out[10] = tr[10]; out[11] = now; }
+        if (warp == kRingWarp) out[12] = tr[12];
     }
     umma::tc_fence_before();
     __syncthreads();
@@ -1147,6 +1203,7 @@ void conv(const Plan& P, const ConvArgs& c, cudaStream_t s) {
     k.tma_gather = g_tma_gather;
     k.l1_gather = g_l1_gather;
     k.ablate = g_ablate;
+    k.trace = 0;
     k.a_hi = c.x.hi;
     k.a_lo = c.x.lo;
     k.chunks = c32 ? 1 : Cin / 64;
@@ -1222,6 +1279,7 @@ void conv(const Plan& P, const ConvArgs& c, cudaStream_t s) {
 
     if (has_rare) {
         KArgs r = k;
+        r.trace = g_trace_on == 2;
         if (k.chunks == 1) {  // a pair tile is one MMA step: one accumulator group (no change of the result), more buffers
             r.G = 1;
             r.nbuf = std::max(1, std::min(4, 512 / (2 * N)));
@@ -1244,6 +1302,7 @@ void conv(const Plan& P, const ConvArgs& c, cudaStream_t s) {
     }
     if (P.mode == kModeStationary) {
         KArgs o = k;
+        o.trace = g_trace_on == 1;
         o.gidx = P.gidx.get();
         o.num_tiles = (int)P.T;
         o.D = P.D;
@@ -1350,6 +1409,16 @@ void scale_rows(H2View x, int64_t V, const float* row_scale, H2View out, cudaStr
         ASRB_CHECK_LAUNCH();
     }
     zero_last_row(out, s);
+}
+
+void trace_read(unsigned* host, int ctas, cudaStream_t s) {
+#ifdef GX_TRACE
+    ASRB_CUDA(cudaStreamSynchronize(s));
+    ASRB_CUDA(cudaMemcpyFromSymbol(host, g_trace, sizeof(unsigned) * kTraceSlots * std::min(ctas, 256)));
+#else
+    (void)host, (void)ctas, (void)s;
+    throw Error(kInvalidArgument, "gx trace: the library was built without the instrumentation (make TRACE=1)");
+#endif
 }
 
 int overflow_flag_read_and_clear(cudaStream_t s) {

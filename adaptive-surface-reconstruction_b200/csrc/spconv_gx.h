@@ -90,6 +90,9 @@ void set_l1_gather(int v);
 void set_max_stages(int v);
 void set_single_tmem(int v);
 void set_one_team(int v);
+void set_trace(int v);
+// dev: 16 unsigned counters per CTA (<= 256 CTAs) of the last traced launch, see spconv_gx.cu
+void trace_read(unsigned* host, int ctas, cudaStream_t s);
 void set_ablate(int v);  // timing experiments only
 void conv(const Plan& P, const ConvArgs& a, cudaStream_t s);
 

@@ -216,6 +216,10 @@ int asr_gx_conv(const asr_gx_plan* plan, const void* d_x, int in_channels, int x
                 int out_lo, float* d_out_f32, int out_f32_pitch, float* d_pairbuf, void* stream);
 /* 1 if a conversion to the split-half format saturated (|x| > 65504) since the last call; synchronises */
 int asr_gx_overflow(void* stream, int* flag);
+/* Development aid (option "gx_trace" = 1): 16 cycle counters per CTA (first `ctas` <= 256 CTAs) of the most recent
+ * asr_gx_conv kernel launch — how long one thread of every warp role waited on each of its barriers; the slots
+ * are listed in csrc/spconv_gx.cu.  Host array of 16 * ctas unsigned.  No reference counterpart. */
+int asr_gx_trace(void* stream, int ctas, unsigned* counters);
 
 /* ---------------------------------------------------------------- multi-GPU sharding helpers
  * The reference is single-process; these serve the sharded form of the path (one process per GPU, geometry

@@ -43,5 +43,5 @@ def _reset_kernel_options(request):
         import torch
         if torch.cuda.is_available():
             from asr_b200 import _lib
-            for name in ("gx_acc_groups", "gx_tma_gather", "gx_l1_gather", "gx_max_stages", "gx_ablate", "gx_single_tmem", "gx_one_team"):
+            for name in ("gx_acc_groups", "gx_tma_gather", "gx_l1_gather", "gx_max_stages", "gx_ablate", "gx_single_tmem", "gx_one_team", "gx_trace"):
                 _lib.set_option(name, 0)

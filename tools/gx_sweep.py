@@ -29,7 +29,7 @@ def timeit(fn, reps=5):
     return e0.elapsed_time(e1) / reps
 
 # gx_ablate (timing only, garbage results): 1 no filter copies, 2 no pair-buffer reads, 4 no row gathers, 8 no stores, 16 no MMAs
-configs = [dict(), dict(gx_one_team=1)] + [dict(gx_ablate=v) for v in (2, 8, 16, 31)]
+configs = [dict()]
 for lev, cin, cout in shapes:
     plan = plans[lev]
     V = plan.num_out
