@@ -278,11 +278,7 @@ def run_block(block, x, plan, importance, scratch, out=None, out_f32=None, res=N
     return y, out_imp
 
 
-def build_plans(input_dict, levels):
-    """gx plans of all neighbour tables (cached in the dict); ONE host synchronisation for all of them."""
-    cache = input_dict.get("_asr_gx_plans")
-    if cache is not None:
-        return cache
+def _begin_plans(input_dict, levels):
     d = input_dict
     V = [d["neighbors_row_splits%d" % i].shape[0] - 1 for i in range(levels)]
     P = {"nb": [], "up": [], "down": [], "V": V}
@@ -295,11 +291,53 @@ def build_plans(input_dict, levels):
         inv = ops.invert_neighbors_list(V[i + 1], ui, us, uk)
         P["down"].append(Plan(inv.neighbors_index, inv.neighbors_attributes, inv.neighbors_row_splits, V[i], 9,
                               MODE_STATIONARY))
+    return P
+
+
+def _finish_plans(P):
     for group in ("nb", "up", "down"):
         for p in P[group]:
             p.finish()
+
+
+def build_plans(input_dict, levels):
+    """gx plans of all neighbour tables (cached in the dict); ONE host synchronisation for all of them.
+    If begin_plans_async() started them on the side stream, this joins that work."""
+    cache = input_dict.get("_asr_gx_plans")
+    if cache is not None:
+        return cache
+    pending = input_dict.pop("_asr_gx_plans_pending", None)
+    if pending is not None:
+        finish_plans_async(input_dict, pending)
+        P, side, done = pending["plans"], pending["side"], pending["done"]
+        torch.cuda.current_stream().wait_event(done)
+    else:
+        P = _begin_plans(input_dict, levels)
+        _finish_plans(P)
     input_dict["_asr_gx_plans"] = P
     return P
+
+
+def begin_plans_async(input_dict, levels, side):
+    """Start the plans of all tables on `side` (the tables were produced on the current stream): the many small
+    kernels of the plan construction then run beside the aggregation search instead of in front of the U-Net."""
+    main = torch.cuda.current_stream()
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        P = _begin_plans(input_dict, levels)
+    input_dict["_asr_gx_plans_pending"] = {"plans": P, "side": side, "done": None}
+
+
+def finish_plans_async(input_dict, pending=None):
+    """Second phase on the side stream (call it once the host has passed a synchronisation point after
+    begin_plans_async, e.g. after the search: the per-table counts are then on the host already)."""
+    pending = pending or input_dict.get("_asr_gx_plans_pending")
+    if pending is None or pending["done"] is not None:
+        return
+    with torch.cuda.stream(pending["side"]):
+        _finish_plans(pending["plans"])
+        pending["done"] = torch.cuda.Event()
+        pending["done"].record(pending["side"])
 
 
 def unet(net, feats1, input_dict, taps=None, ctx=None, x0=None, code=None):

@@ -105,6 +105,11 @@ def build_input_dict(points, normals, radii, bb_min, bb_max, levels=5, radius_sc
         for k, v in g.items():
             if k != "voxel_keys":
                 d[k + str(i)] = v
+    plans_async = (K is ops and ops.SPARSE_CONV_BACKEND == "gx" and not timer.enabled and len(grids) == levels
+                   and "neighbors_row_splits0" in d)
+    if plans_async:  # the gx plans of the U-Net's tables are built beside the search, on the side stream
+        from . import gx
+        gx.begin_plans_async(d, levels, side_stream())
     if "voxel_centers0" not in d:  # empty tree
         d["voxel_centers0"] = torch.zeros((0, 3), dtype=torch.float32, device=points.device)
         d["voxel_sizes0"] = torch.zeros(0, dtype=torch.float32, device=points.device)
@@ -113,6 +118,8 @@ def build_input_dict(points, normals, radii, bb_min, bb_max, levels=5, radius_sc
     d["aggregation_neighbors_dist"] = dist
     d["aggregation_row_splits"] = rs
     d["aggregation_scale_compat"] = K.scale_compatibility(d["voxel_sizes0"], radii, idx, rs)
+    if plans_async:
+        gx.finish_plans_async(d)
     timer.lap("search")
     return d, duals, tree
 

@@ -349,11 +349,18 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(int n, int k) {
     return (uint32_t)((n >> 3) * 1024 + (n & 7) * 128 + ((((k >> 3) ^ n) & 7) << 4) + (k & 7) * 2);
 }
 
+// Operand layout rule.  64-channel stages: an A stage = hi tile + lo tile (2 x 16 KB), B = [B_hi | B_lo] (2 N x 128
+// bytes).  32-channel stages ("c32"): ONE tile per operand whose 128-byte rows hold [32 hi halves | 32 lo halves].
+// c32 is used for 32 input channels.  (Measured and rejected: c32 stages also for N = 128, which makes room for a
+// second staging tile so that the rare sums run ahead of the epilogue — twice the stages, barrier round trips and
+// MMA instructions cost more than that overlap gains: level-1 128->128 0.95 -> 1.05 ms, level-2 256->128 0.35 -> 0.48 ms.)
+__host__ __device__ __forceinline__ bool use_c32(int Cin, int N) { return (void)N, Cin == 32; }
+
 __global__ void __launch_bounds__(256)
 pack_filters_kernel(const float* __restrict__ W, int K, int Cin, int Cout, int col0, int ncols, int N, float scale,
                     uint8_t* __restrict__ out) {
-    const bool c32 = Cin == 32;
-    const int chunks = c32 ? 1 : Cin / 64;
+    const bool c32 = use_c32(Cin, N);
+    const int chunks = c32 ? Cin / 32 : Cin / 64;
     const int kc = c32 ? 32 : 64;
     const size_t chunk_bytes = (size_t)(c32 ? 1 : 2) * N * 128;
     const long long total = (long long)K * chunks * N * kc;
@@ -384,7 +391,7 @@ static int padded_n(int ncols) { return ((ncols + 15) / 16) * 16; }
 
 size_t packed_filter_bytes(int K, int Cin, int ncols) {
     const int N = padded_n(ncols);
-    return Cin == 32 ? (size_t)K * N * 128 : (size_t)K * (Cin / 64) * 2 * N * 128;
+    return (size_t)K * (Cin / 32) * N * 128;  // the same for both operand layouts
 }
 
 void pack_filters(const float* W, int K, int Cin, int Cout, int col0, int ncols, int scale_exp, void* out,
@@ -392,7 +399,7 @@ void pack_filters(const float* W, int K, int Cin, int Cout, int col0, int ncols,
     ASRB_REQUIRE(Cin == 32 || (Cin >= 64 && Cin % 64 == 0), "gx: in_channels must be 32 or a multiple of 64");
     ASRB_REQUIRE(ncols >= 1 && ncols <= 256 && col0 >= 0 && col0 + ncols <= Cout, "gx: bad output column range");
     const int N = padded_n(ncols);
-    const long long total = (long long)K * (Cin == 32 ? 1 : Cin / 64) * N * (Cin == 32 ? 32 : 64);
+    const long long total = (long long)K * Cin * N;
     pack_filters_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, s>>>(
             W, K, Cin, Cout, col0, ncols, N, ldexpf(1.f, scale_exp), (uint8_t*)out);
     ASRB_CHECK_LAUNCH();
@@ -632,10 +639,13 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int r = warp * 32 + 4 * i + rl;
-                    src[i] = a.x + (size_t)g[i] * a.x_pitch + cj * 8;
+                    src[i] = a.x + (size_t)g[i] * a.x_pitch;
                     nbytes[i] = g[i] == a.zero_row ? 0u : 16u;
                     dst[i] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((cj ^ r) & 7) << 4));
                 }
+                // column of this lane's 16-byte piece: c32 rows are [32 hi | 32 lo] of the chunk's 32 channels
+                const int col_hi = C32 ? (cj < 4 ? a.a_hi + cj * 8 : a.a_lo + (cj - 4) * 8) : a.a_hi + cj * 8;
+                const int col_lo = a.a_lo + cj * 8, cstep = C32 ? 32 : 64;
                 for (int c = 0; c < a.chunks; ++c) {
                     GX_TIMED(warp == 0 && lane == 0, 1, umma::mbar_wait(&bar_empty[st], ph ^ 1));
                     const uint32_t stage = sbase + (uint32_t)st * a.stage_bytes;
@@ -653,20 +663,20 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                     } else if (a.l1_gather) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            umma::cp_async16_ca(stage + dst[i], src[i] + a.a_hi + c * 64, nbytes[i]);
+                            umma::cp_async16_ca(stage + dst[i], src[i] + col_hi + c * cstep, nbytes[i]);
                         if (!C32) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
-                                umma::cp_async16_ca(stage + kATile + dst[i], src[i] + a.a_lo + c * 64, nbytes[i]);
+                                umma::cp_async16_ca(stage + kATile + dst[i], src[i] + col_lo + c * cstep, nbytes[i]);
                         }
                     } else {
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            umma::cp_async16_cg(stage + dst[i], src[i] + a.a_hi + c * 64, nbytes[i]);
+                            umma::cp_async16_cg(stage + dst[i], src[i] + col_hi + c * cstep, nbytes[i]);
                         if (!C32) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
-                                umma::cp_async16_cg(stage + kATile + dst[i], src[i] + a.a_lo + c * 64, nbytes[i]);
+                                umma::cp_async16_cg(stage + kATile + dst[i], src[i] + col_lo + c * cstep, nbytes[i]);
                         }
                     }
                     umma::cp_async_arrive_noinc(&bar_full[st]);
@@ -1186,13 +1196,15 @@ size_t pairbuf_floats(const Plan& P, int ncols) {
 
 void conv(const Plan& P, const ConvArgs& c, cudaStream_t s) {
     ASRB_REQUIRE(P.finished, "gx conv: the plan is not finished");
+    if (P.gidx.s != s || P.rare_rs.s != s) const_cast<Plan&>(P).rehome(s);
     const int Cin = c.x.C;
-    const bool c32 = Cin == 32;
-    ASRB_REQUIRE(c32 || (Cin >= 64 && Cin % 64 == 0), "gx conv: in_channels must be 32 or a multiple of 64");
+    ASRB_REQUIRE(Cin == 32 || (Cin >= 64 && Cin % 64 == 0), "gx conv: in_channels must be 32 or a multiple of 64");
+    const bool c32 = use_c32(Cin, padded_n(c.ncols));
     ASRB_REQUIRE(c.ncols % 8 == 0 && c.ncols >= 8 && c.ncols <= 128,
                  "gx conv: output columns must be a multiple of 8, <= 128 per call (wider banks run as column groups)");
     ASRB_REQUIRE(c.x.rows == P.V_in + 1, "gx conv: the input view must hold the plan's input rows + the zero row");
-    ASRB_REQUIRE(!c32 || (c.x.hi % 64 == 0 && c.x.lo == c.x.hi + 32), "gx conv: a 32-channel input must be a plain [hi | lo] row");
+    // the TMA gather form copies 128 contiguous bytes per row: a plain [32 hi | 32 lo] row only
+    const bool tma_ok = !c32 || (Cin == 32 && c.x.hi % 64 == 0 && c.x.lo == c.x.hi + 32);
     ASRB_REQUIRE((c.out.p != nullptr) != (c.out_f32 != nullptr), "gx conv: exactly one of the h2 / fp32 outputs");
     if (P.V == 0) return;
     const int N = padded_n(c.ncols);
@@ -1200,13 +1212,13 @@ void conv(const Plan& P, const ConvArgs& c, cudaStream_t s) {
     k.V = (int)P.V;
     k.x = c.x.p;
     k.x_pitch = c.x.pitch;
-    k.tma_gather = g_tma_gather;
+    k.tma_gather = g_tma_gather && tma_ok;
     k.l1_gather = g_l1_gather;
     k.ablate = g_ablate;
     k.trace = 0;
     k.a_hi = c.x.hi;
     k.a_lo = c.x.lo;
-    k.chunks = c32 ? 1 : Cin / 64;
+    k.chunks = c32 ? Cin / 32 : Cin / 64;
     k.wp = (const uint8_t*)c.wp;
     k.chunk_bytes = (uint32_t)((c32 ? 1 : 2) * N * 128);
     k.slot_bytes = (unsigned long long)k.chunks * k.chunk_bytes;

@@ -43,6 +43,11 @@ struct Plan {
     DevBuf<int32_t> pt_gidx;   // [tiles][128] gather rows
     DevBuf<int32_t> pt_out;    // [tiles][128] pair-buffer row / output row, -1 = padding
     DevBuf<int> pt_count;      // device scalar: number of pair tiles
+    // a plan may be built on one stream and used on another (after the caller's event wait): its buffers are
+    // then FREED in the order of the stream that uses them
+    void rehome(cudaStream_t s) {
+        gidx.s = rare_rs.s = rare_in.s = pt_slot.s = pt_gidx.s = pt_out.s = pt_count.s = s;
+    }
     // begin() state kept for finish()
     const int32_t* d_idx = nullptr;
     const uint8_t* d_slot = nullptr;
