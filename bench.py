@@ -504,7 +504,7 @@ def main():
                          "gpurun_out/r2_parity_<points>.json)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--backend", default="gx", choices=["gx", "tensor", "fp32"],
-                    help="sparse-conv path: gx = split-half activations + TMA-gather tcgen05 kernel (default), "
+                    help="sparse-conv path: gx = split-half activations + cp.async-gather tcgen05 kernel (default), "
                          "tensor = round-1 pair-major 3xTF32 kernel, fp32 = FMA kernel")
     ap.add_argument("--profile-run", action="store_true",
                     help="for runs under ncu: no minimum warm-up, no e2e leg; the printed numbers are NOT bench values")
