@@ -539,12 +539,14 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                 umma::mbar_init(&bar_tempty[i], kEpilogueWarps / a.teams);
             }
             for (int i = 0; i < 2; ++i) {
-                umma::mbar_init(&bar_rfull[i], kRareWarps);
-                umma::mbar_init(&bar_rempty[i], kEpilogueWarps / a.teams);
+                // shared-memory hand-overs between warps: EVERY lane arrives after its own accesses (an elected lane behind
+                // __syncwarp is ordered too, but compute-sanitizer's racecheck does not follow that chain)
+                umma::mbar_init(&bar_rfull[i], kRareWarps * 32);
+                umma::mbar_init(&bar_rempty[i], kEpilogueWarps / a.teams * 32);
             }
             for (int i = 0; i < 4; ++i) {
                 umma::mbar_init(&bar_ring_full[i], 1);
-                umma::mbar_init(&bar_ring_empty[i], kRareWarps);
+                umma::mbar_init(&bar_ring_empty[i], kRareWarps * 32);
             }
             umma::fence_barrier_init();
         }
@@ -966,10 +968,7 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                 }
             }
             if (GX_TRACING && e == 0 && lane == 0) tr[7] += GX_CLOCK() - t_co0;
-            if (has_rare) {
-                __syncwarp();
-                if (lane == 0) umma::mbar_arrive(&bar_rempty[rb]);
-            }
+            if (has_rare) umma::mbar_arrive(&bar_rempty[rb]);
         }
         if (GX_TRACING && e == 0 && lane == 0) tr[8] = GX_CLOCK() - t_kernel0;
         if (overflow) atomicOr(&g_overflow_flag, 1);
@@ -1104,16 +1103,14 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
                         if (p < pe) break;  // the row continues in the next chunk
                         finish_row();
                     }
-                    __syncwarp();
-                    if (lane == 0) umma::mbar_arrive(&bar_ring_empty[rsl]);
+                    umma::mbar_arrive(&bar_ring_empty[rsl]);
                     if (++rsl == RS) {
                         rsl = 0;
                         rph ^= 1;
                     }
                 }
                 while (cr < kTM) finish_row();  // rows without (further) pairs
-                __syncwarp();
-                if (lane == 0) umma::mbar_arrive(&bar_rfull[rb]);
+                umma::mbar_arrive(&bar_rfull[rb]);
             }
         }
     }

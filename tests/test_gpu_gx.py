@@ -175,3 +175,19 @@ def test_unet_on_gx_matches_oracle(levels, cloud, n, monkeypatch):
     monkeypatch.setattr(ops, "SPARSE_CONV_BACKEND", "tensor")
     code_tc = net.unet((feats, imp), d)
     assert (code_tc - code).abs().max().item() <= TOL * max(1.0, rcode.abs().max().item())
+
+
+def test_dev_options_and_trace_guard():
+    """unknown options are refused; the per-role trace of the gx kernel exists only in the instrumented build
+    (make TRACE=1) and says so instead of returning stale counters"""
+    import ctypes
+    from asr_b200 import _lib
+    with pytest.raises(ValueError):
+        _lib.set_option("no_such_option", 1)
+    for name in ("gx_acc_groups", "gx_tma_gather", "gx_l1_gather", "gx_max_stages", "gx_ablate", "gx_single_tmem",
+                 "gx_one_team", "gx_trace"):
+        _lib.set_option(name, 0)
+    buf = (ctypes.c_uint * 16)()
+    rc = _lib.lib().asr_gx_trace(None, 1, buf)
+    if rc != 0:
+        assert b"TRACE=1" in _lib.lib().asr_last_error()

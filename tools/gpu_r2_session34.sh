@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( time timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" ) > gpurun_out/s34_racecheck_smoke.log 2>&1
+( timeout 600 python tools/gx_sweep.py 10000000 ) > gpurun_out/s34_sweep.log 2>&1
+( time timeout 900 python -m pytest tests/test_gpu_gx.py tests/test_gpu_configs.py -m gpu -x -q 2>&1 | tail -25 ) > gpurun_out/s34_pytest.log 2>&1
+( timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/s34_bench.json ) 2> gpurun_out/s34_bench.err
+echo done
