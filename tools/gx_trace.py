@@ -1,4 +1,5 @@
-"""GPU box: per-role wait cycles of the gx convolution kernel (dev option gx_trace) on the bench cloud's tables."""
+"""GPU box: per-role wait cycles of the gx convolution kernel (dev option gx_trace) on the bench cloud's tables.
+Needs the instrumented library: touch csrc/spconv_gx.cu && make -C adaptive-surface-reconstruction_b200/csrc TRACE=1"""
 import sys, os, ctypes as C
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
