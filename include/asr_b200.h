@@ -177,11 +177,13 @@ int asr_invert_neighbors_list(int64_t num_points, const int32_t* d_inp_neighbors
  * `sparse_conv` + bias + ReLU): the same convolution as asr_sparse_conv for activations that stay on the device
  * between layers in a split-half format — a [V, C] tensor is stored as rows of `pitch` fp16 values holding hi =
  * fp16(x) at columns [hi, hi + C) and lo = fp16(x - hi) at [lo, lo + C) (4 bytes per element like fp32); buffers
- * have V + 1 rows, the last one all zero.  csrc/spconv_gx.cu describes the kernel (TMA row gather, fp16 hi/lo
- * tcgen05 MMAs into TMEM, output-stationary dense slots + pair-major rare slots, fused epilogue).
+ * have V + 1 rows, the last one all zero.  csrc/spconv_gx.cu describes the kernel (cp.async row gather, fp16 hi/lo
+ * tcgen05 MMAs into TMEM, output-stationary dense slots + pair-major rare slots, fused and coalesced epilogue).
  * mode 0: within-grid (K = 55) and down (K = 9, inverted up table) tables; mode 1: up tables (one entry per row).
  * _plan_begin queues the counting kernels, _plan_finish (one host synchronisation, shared by all plans begun
- * before it) completes the plan and returns the number of rare entries (pair-buffer rows). */
+ * before it) completes the plan and returns the number of rare entries (pair-buffer rows).  A plan may be built on
+ * another stream than the one its convolutions run on (the caller orders the two with an event): from its first
+ * convolution on, its buffers are released in the order of that convolution's stream. */
 typedef struct asr_gx_plan asr_gx_plan;
 /* d_row_map (may be NULL): the plan covers only the table rows d_row_map[0 .. num_out) (one rank's rows of a
  * sharded grid level, ascending); outputs / normalisers / residuals stay indexed by table row.  The array must
