@@ -393,6 +393,7 @@ class SpatialShardedOps:
         cut = torch.tensor([(k * V) // self.world for k in range(1, self.world)], dtype=torch.int64, device=codes.device)
         self._frame = (lo, 1023.0 / ext, codes[cut].contiguous())
         self._own = {V: self._make_ownership(centers, sizes)}
+        self._own_level = {V: 0}
         return self._own[V]
 
     def prepare(self, input_dict, levels):
@@ -403,6 +404,14 @@ class SpatialShardedOps:
                 continue
             if c.shape[0] not in self._own:
                 self._own[c.shape[0]] = self._make_ownership(c, input_dict["voxel_sizes%d" % l])
+                self._own_level = getattr(self, "_own_level", {})
+                self._own_level[c.shape[0]] = l
+            elif getattr(self, "_own_level", {}).get(c.shape[0], l) != l:
+                # ownership is looked up by a level's row count (the tensors carry no level tag): two sharded levels
+                # of equal size would silently share one ownership — refuse instead
+                raise NotImplementedError("sharded round-1 path: grid levels %d and %d both have %d voxels; use the gx "
+                                          "backend (shard_gx keys ownership by level)" %
+                                          (self._own_level[c.shape[0]], l, c.shape[0]))
 
     # ------------------------------------------------------------------ helpers
     @staticmethod
@@ -548,6 +557,7 @@ class SpatialShardedOps:
     def multi_radius_search(self, points, queries, radii, frame=None):
         V = queries.shape[0]
         self._own, self._frame, self._agg = {}, None, None
+        self._own_level = {}
         if self.world == 1 or V < self.min_rows:
             return self.base.multi_radius_search(points, queries, radii, frame=frame)
         own = self._level0(queries, radii)

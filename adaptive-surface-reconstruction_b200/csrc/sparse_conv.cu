@@ -503,11 +503,13 @@ void row_importance(const float* imp, const int32_t* idx, const int64_t* splits,
 template <int TN>
 static void launch_tiles(const ConvPlan& P, const TileArgs& a, cudaStream_t s) {
     const size_t smem = (size_t)(2 * TM * LDA + 2 * KC * TN) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};  // per device (function attributes are per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
         ASRB_CUDA(cudaFuncSetAttribute(sparse_conv_tile_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
-        configured = true;
+        configured[dev & 63] = true;
     }
     dim3 grid((unsigned)P.max_tiles, (unsigned)((a.Cout + TN - 1) / TN));
     char label[96];
