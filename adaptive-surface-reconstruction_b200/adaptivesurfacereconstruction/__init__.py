@@ -109,7 +109,7 @@ def reconstruct_surface(points, normals, radii, point_radius_scale=1.0, density_
     sparsest `density_percentile_threshold` percent of the points are dropped (see
     asr_b200.ops.density_inlier for the one deliberate difference to the reference).
     `model` (an asr_b200.model.UNet) overrides the model.pt lookup.
-    Limit of this backend: point_radius_estimation_knn <= 32 (ValueError above; the reference accepts any k)."""
+    Limit of this backend: point_radius_estimation_knn <= 64 (ValueError above; the reference accepts any k)."""
     points = _f32(points, "points", "points must have shape [num_points,3]", 2, 3)
     normals = np.ascontiguousarray(normals, dtype=np.float32)
     if normals.ndim != 2 or normals.shape != points.shape:

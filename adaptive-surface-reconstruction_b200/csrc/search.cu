@@ -609,7 +609,7 @@ void scale_compat(const float* d_sizes, const float* d_radii, const int32_t* d_i
 //      are kept as a sorted list spread over the lanes (insertion by ballot + shuffle);
 //   3. the k-th distance is exact once it does not exceed the distance to the block's boundary
 //      (>= one cell); otherwise the cell size doubles and the block is rescanned.
-// k <= 32 (the reference's default is 24).
+// k <= 64 (the reference's default is 24): one sorted list over the lanes for k <= 32, two for 32 < k <= 64.
 namespace {
 
 __device__ __forceinline__ long long lower_bound_code(const Key* __restrict__ a, long long n, Key k) {
@@ -622,7 +622,7 @@ __device__ __forceinline__ long long lower_bound_code(const Key* __restrict__ a,
     return lo;
 }
 
-template <bool INLIER>
+template <bool INLIER, bool WIDE>  // WIDE: 32 < k <= 64, a second sorted list (ranks 32..63) over the lanes
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 knn_kernel(const Key* __restrict__ codes, const float4* __restrict__ spts, long long n, int k, float cell0,
            float* __restrict__ out_radius, const float* __restrict__ radii, float fraction, int vote_limit,
@@ -647,6 +647,11 @@ knn_kernel(const Key* __restrict__ codes, const float4* __restrict__ spts, long 
     }
     float best_d = __int_as_float(0x7f800000);  // sorted ascending over the lanes
     int best_i = -1;
+    float best_d1 = __int_as_float(0x7f800000);  // WIDE: ranks 32 .. 63
+    int best_i1 = -1;
+    auto kth_value = [&]() {
+        return (WIDE && k > 32) ? __shfl_sync(0xffffffffu, best_d1, k - 33) : __shfl_sync(0xffffffffu, best_d, k - 1);
+    };
     for (;;) {
         // 2. windows of the 27 cells around the point at this scale
         const int cells_per_axis = 1 << (kGridBits - sh);
@@ -675,8 +680,8 @@ knn_kernel(const Key* __restrict__ codes, const float4* __restrict__ spts, long 
         if (lane == 0) s_pre[warp][0] = 0;
         __syncwarp();
         const int total = __shfl_sync(0xffffffffu, pre, 31);
-        best_d = __int_as_float(0x7f800000);
-        best_i = -1;
+        best_d = best_d1 = __int_as_float(0x7f800000);
+        best_i = best_i1 = -1;
         for (int t0 = 0; t0 < total; t0 += 32) {
             const int t = t0 + lane;
             float d2 = __int_as_float(0x7f800000);
@@ -691,7 +696,7 @@ knn_kernel(const Key* __restrict__ codes, const float4* __restrict__ spts, long 
                 d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
                 pi = __float_as_int(p.w);
             }
-            const float kth = __shfl_sync(0xffffffffu, best_d, k - 1);
+            const float kth = kth_value();
             unsigned acc = __ballot_sync(0xffffffffu, d2 < kth);
             while (acc) {
                 const int src = __ffs(acc) - 1;
@@ -699,10 +704,31 @@ knn_kernel(const Key* __restrict__ codes, const float4* __restrict__ spts, long 
                 const float c = __shfl_sync(0xffffffffu, d2, src);
                 const int ci = __shfl_sync(0xffffffffu, pi, src);
                 // later candidates of the batch may have fallen behind the updated k-th value
-                if (!(c < __shfl_sync(0xffffffffu, best_d, k - 1))) continue;
-                const int pos = __popc(__ballot_sync(0xffffffffu, best_d <= c));
+                if (!(c < kth_value())) continue;
+                int pos = __popc(__ballot_sync(0xffffffffu, best_d <= c));
                 const float up_d = __shfl_up_sync(0xffffffffu, best_d, 1);
                 const int up_i = __shfl_up_sync(0xffffffffu, best_i, 1);
+                if (WIDE) {
+                    // the second list: shifted as a whole (rank 31 moves into its lane 0) or from the insertion point on
+                    const int pos1 = __popc(__ballot_sync(0xffffffffu, best_d1 <= c));
+                    const float up_d1 = __shfl_up_sync(0xffffffffu, best_d1, 1);
+                    const int up_i1 = __shfl_up_sync(0xffffffffu, best_i1, 1);
+                    const float last_d = __shfl_sync(0xffffffffu, best_d, 31);
+                    const int last_i = __shfl_sync(0xffffffffu, best_i, 31);
+                    if (pos < 32) {
+                        best_d1 = lane == 0 ? last_d : up_d1;
+                        best_i1 = lane == 0 ? last_i : up_i1;
+                    } else {
+                        if (lane > pos1) {
+                            best_d1 = up_d1;
+                            best_i1 = up_i1;
+                        } else if (lane == pos1) {
+                            best_d1 = c;
+                            best_i1 = ci;
+                        }
+                        pos = 64;  // nothing changes in the first list
+                    }
+                }
                 if (lane > pos) {
                     best_d = up_d;
                     best_i = up_i;
@@ -714,20 +740,30 @@ knn_kernel(const Key* __restrict__ codes, const float4* __restrict__ spts, long 
         }
         __syncwarp();
         // 3. exact once the k-th distance lies inside the scanned block
-        const float kth = __shfl_sync(0xffffffffu, best_d, k - 1);
+        const float kth = kth_value();
         const float cover = cell0 * (float)(1 << sh) * 0.9999f;
         if (sh >= kGridBits || kth <= cover * cover) break;
         ++sh;
     }
-    const int valid = __popc(__ballot_sync(0xffffffffu, best_i >= 0 && lane < k));
+    const int valid0 = __popc(__ballot_sync(0xffffffffu, best_i >= 0 && lane < k));
+    const int valid1 = WIDE ? __popc(__ballot_sync(0xffffffffu, best_i1 >= 0 && lane + 32 < k)) : 0;
+    const int valid = valid0 + valid1;
     const long long self = __float_as_int(q.w);
     if (!INLIER) {
-        const float dmax = valid > 0 ? __shfl_sync(0xffffffffu, best_d, max(valid, 1) - 1) : 0.f;
+        float dmax = valid0 > 0 ? __shfl_sync(0xffffffffu, best_d, max(valid0, 1) - 1) : 0.f;
+        if (WIDE) {
+            const float d1 = __shfl_sync(0xffffffffu, best_d1, max(valid1, 1) - 1);
+            if (valid1 > 0) dmax = d1;
+        }
         if (lane == 0) out_radius[self] = sqrtf(dmax);
     } else {
         const float limit = __fmul_rn(radii[self], fraction);
-        const bool vote = lane < valid && radii[best_i] < limit;
-        const int votes = __popc(__ballot_sync(0xffffffffu, vote));
+        const bool vote = lane < valid0 && radii[best_i] < limit;
+        int votes = __popc(__ballot_sync(0xffffffffu, vote));
+        if (WIDE) {
+            const bool vote1 = lane < valid1 && radii[max(best_i1, 0)] < limit;
+            votes += __popc(__ballot_sync(0xffffffffu, vote1));
+        }
         if (lane == 0) out_inlier[self] = votes < vote_limit ? 1 : 0;
     }
 }
@@ -778,22 +814,31 @@ void knn_build(Search& S, const float* d_points, int64_t n, cudaStream_t s) {
 }
 
 void knn_radius(const Search& S, int k, float* d_out, cudaStream_t s) {
-    ASRB_REQUIRE(k >= 1 && k <= 32, "asr_b200 kNN: k must be in [1, 32] (the reference default is 24; the warp-wide candidate list holds 32 entries)");
+    ASRB_REQUIRE(k >= 1 && k <= 64, "asr_b200 kNN: k must be in [1, 64] (the reference default is 24; the warp-wide candidate lists hold 64 entries)");
     if (S.n == 0) return;
     ProfileScope prof("knn_radius", s);
-    knn_kernel<false><<<grid_for(S.n, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
-            S.codes.get(), (const float4*)S.spts.get(), S.n, k, 1.0f / S.frame_inv_h, d_out, nullptr, 0.f, 0, nullptr);
+    if (k <= 32)
+        knn_kernel<false, false><<<grid_for(S.n, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
+                S.codes.get(), (const float4*)S.spts.get(), S.n, k, 1.0f / S.frame_inv_h, d_out, nullptr, 0.f, 0, nullptr);
+    else
+        knn_kernel<false, true><<<grid_for(S.n, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
+                S.codes.get(), (const float4*)S.spts.get(), S.n, k, 1.0f / S.frame_inv_h, d_out, nullptr, 0.f, 0, nullptr);
     ASRB_CHECK_LAUNCH();
 }
 
 void knn_inlier(const Search& S, const float* d_radii, float fraction, int k, int outlier_threshold, uint8_t* d_out,
                 cudaStream_t s) {
-    ASRB_REQUIRE(k >= 1 && k <= 32, "asr_b200 kNN: k must be in [1, 32] (the reference default is 24; the warp-wide candidate list holds 32 entries)");
+    ASRB_REQUIRE(k >= 1 && k <= 64, "asr_b200 kNN: k must be in [1, 64] (the reference default is 24; the warp-wide candidate lists hold 64 entries)");
     if (S.n == 0) return;
     ProfileScope prof("knn_inlier", s);
-    knn_kernel<true><<<grid_for(S.n, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
-            S.codes.get(), (const float4*)S.spts.get(), S.n, k, 1.0f / S.frame_inv_h, nullptr, d_radii, fraction,
-            outlier_threshold, d_out);
+    if (k <= 32)
+        knn_kernel<true, false><<<grid_for(S.n, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
+                S.codes.get(), (const float4*)S.spts.get(), S.n, k, 1.0f / S.frame_inv_h, nullptr, d_radii, fraction,
+                outlier_threshold, d_out);
+    else
+        knn_kernel<true, true><<<grid_for(S.n, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
+                S.codes.get(), (const float4*)S.spts.get(), S.n, k, 1.0f / S.frame_inv_h, nullptr, d_radii, fraction,
+                outlier_threshold, d_out);
     ASRB_CHECK_LAUNCH();
 }
 

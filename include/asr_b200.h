@@ -297,7 +297,7 @@ void asr_contour_triangles_destroy(void* handle);
  * _k_radius: sqrt of the largest of the k smallest squared distances, the point itself included
  * (ComputeKRadius :30-52); _inlier: 1 unless at least `outlier_threshold` of the k nearest points
  * have a radius < radius_fraction * own radius (ComputeInlier :54-85); counts: number of points
- * with |p - p_i|^2 < r_i^2 (ComputeRadiusNeighbors :87-105).  k <= 32.  The handle is destroyed
+ * with |p - p_i|^2 < r_i^2 (ComputeRadiusNeighbors :87-105).  k <= 64.  The handle is destroyed
  * with asr_radius_search_destroy. */
 int asr_kdtree_create(const float* d_points, int64_t num_points, void* stream, asr_search** out);
 int asr_kdtree_k_radius(asr_search* tree, int k, float* d_out, void* stream);

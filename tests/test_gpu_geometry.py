@@ -200,7 +200,7 @@ def test_kdtree_matches_float32_knn_oracle():
     for name, c in (("blob", clouds.adaptive_blob(20000, seed=5)), ("sphere", clouds.sphere(6000, seed=1))):
         pts = c["points"]
         tree = asr.KDTree(pts)
-        for k in (24, 1, 32, 7):
+        for k in (24, 1, 32, 7, 33, 48, 64):  # > 32: the two-list form of the kernel
             r = tree.compute_k_radius(k)
             assert r.dtype == np.float32 and np.array_equal(r, ops_cpu.k_radius(pts, k)), (name, k)
         r24 = tree.compute_k_radius(24)
@@ -211,10 +211,14 @@ def test_kdtree_matches_float32_knn_oracle():
         assert 0.0 < ref.mean() < 1.0
         got3 = tree.compute_inlier(rad, 0.7, 16, 3)
         assert (got3 != ops_cpu.knn_inlier(pts, rad, 0.7, 16, 3)).mean() < 1e-3
+        got4 = tree.compute_inlier(rad, 0.6, 40, 5)
+        assert (got4 != ops_cpu.knn_inlier(pts, rad, 0.6, 40, 5)).mean() < 1e-3
         cnt = tree.compute_radius_neighbors(r24)
         assert isinstance(cnt, list) and np.array_equal(np.asarray(cnt, np.int32), ops_cpu.radius_neighbor_counts(pts, r24))
     with pytest.raises(ValueError):
         asr.KDTree(np.zeros((5, 2), np.float32))
+    with pytest.raises(ValueError):  # the backend's limit (the reference accepts any k)
+        tree.compute_k_radius(65)
 
 
 def test_reconstruct_surface_estimates_radii():
