@@ -190,6 +190,35 @@ class ShardContext(gx.LocalContext):
         self.push_rows(view.buf, level, (view.hi * 2, view.lo * 2), view.C * 2)
 
 
+def first_pair_importances(rs, own_rows, imp_pairs, V0, all_reduce=None):
+    """Quirk 0 on a sharded level 0: the first encoder block reads imp_pairs[v], v < V0, of the GLOBAL
+    pair list (all voxels' pairs in table order).  rs / imp_pairs: row splits and pair importances of this rank's own
+    voxels `own_rows` (ascending table rows); all_reduce(tensor): in-place sum over the ranks (None: one rank).
+    Returns (first [V0] float32, total number of pairs).  Only the few voxels whose pairs fall below V0 are touched
+    (a device-only formulation over ALL local pairs was measured slower: 5.0 vs 3.7 ms at 2 GPUs, 10 M points)."""
+    dev = imp_pairs.device
+    counts = torch.zeros(V0, dtype=torch.int32, device=dev)
+    counts[own_rows] = (rs[1:] - rs[:-1]).to(torch.int32)
+    if all_reduce is not None:
+        all_reduce(counts)
+    start = torch.cumsum(counts.long(), 0) - counts.long()  # first global pair of every voxel
+    total = int(start[-1] + counts[-1]) if V0 else 0
+    first = torch.zeros(V0, dtype=torch.float32, device=dev)
+    s_own = start[own_rows]
+    sel = torch.nonzero(s_own < V0).reshape(-1)  # owned voxels whose pairs can fall into [0, V0)
+    if sel.numel():
+        lo = rs[sel]
+        n = torch.minimum(rs[sel + 1] - lo, V0 - s_own[sel])
+        tot = int(n.sum())
+        if tot:
+            seg = torch.repeat_interleave(torch.arange(sel.numel(), device=dev), n)
+            within = torch.arange(tot, device=dev) - torch.repeat_interleave(torch.cumsum(n, 0) - n, n)
+            first[s_own[sel][seg] + within] = imp_pairs[lo[seg] + within]
+    if all_reduce is not None:
+        all_reduce(first)
+    return first, total
+
+
 def reconstruct_vertices(net, ctx, points, normals, radii, bb_min, bb_max, levels=None, radius_scale=1.0, max_depth=21,
                          contouring_value_threshold=1.0, timer=None):
     """pipeline.reconstruct_vertices on `ctx.world` GPUs (called by every rank with the same cloud).  Returns the same
@@ -233,26 +262,10 @@ def reconstruct_vertices(net, ctx, points, normals, radii, bb_min, bb_max, level
     feats_own = ops.continuous_conv(c.kernel, centers, sizes, c.offset, points, feats_in, None, idx, imp_pairs, rs,
                                     normalize=True, bias=c.bias, relu=True)
     # ---- quirk 0: the first encoder block reads imp_pairs[v] for the GLOBAL pair list (voxels in table order)
-    counts = torch.zeros(V0, dtype=torch.int32, device=points.device)
-    counts[own0_l] = (rs[1:] - rs[:-1]).to(torch.int32)
-    if world > 1:
-        dist.all_reduce(counts, group=ctx.arena.group)
-    start = torch.cumsum(counts.long(), 0) - counts.long()  # first global pair of every voxel
-    if int(start[-1] + counts[-1]) < V0:
+    first, pairs_total = first_pair_importances(
+        rs, own0_l, imp_pairs, V0, (lambda t: dist.all_reduce(t, group=ctx.arena.group)) if world > 1 else None)
+    if pairs_total < V0:
         raise IndexError("fewer aggregation pairs than voxels")
-    first = torch.zeros(V0, dtype=torch.float32, device=points.device)
-    s_own = start[own0_l]
-    sel = torch.nonzero(s_own < V0).reshape(-1)  # owned voxels whose pairs can fall into [0, V0)
-    if sel.numel():
-        lo = rs[sel]
-        n = torch.minimum(rs[sel + 1] - lo, V0 - s_own[sel])
-        tot = int(n.sum())
-        if tot:
-            seg = torch.repeat_interleave(torch.arange(sel.numel(), device=points.device), n)
-            within = torch.arange(tot, device=points.device) - torch.repeat_interleave(torch.cumsum(n, 0) - n, n)
-            first[s_own[sel][seg] + within] = imp_pairs[lo[seg] + within]
-    if world > 1:
-        dist.all_reduce(first, group=ctx.arena.group)
     # ---- features into the symmetric split-half buffer: ONLY the owned rows are written (the other ranks push their
     # rows into this buffer at their own pace), then the halo is pushed
     x0 = ctx.empty(V0, feats_own.shape[1], points.device)
@@ -260,7 +273,7 @@ def reconstruct_vertices(net, ctx, points, normals, radii, bb_min, bb_max, level
     ctx.done(x0, 0)
     d["aggregation_neighbors_index"], d["aggregation_neighbors_dist"], d["aggregation_row_splits"] = idx, dist2, rs
     d["aggregation_scale_compat"] = compat
-    d["aggregation_pairs_total"] = int(start[-1] + counts[-1])
+    d["aggregation_pairs_total"] = pairs_total
     timer.lap("aggregate")
     code = ctx.arena.alloc((V0, 32), torch.float32)
     gx.unet(net, (None, first), d, ctx=ctx, x0=x0, code=code)
