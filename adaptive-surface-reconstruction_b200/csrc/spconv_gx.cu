@@ -71,9 +71,9 @@ constexpr int kRowBlockShift = 15;  // rare entries are grouped by blocks of 2^1
 constexpr int kProducerWarps = 4;
 constexpr int kMmaWarp = kProducerWarps;                  // warps 0-3 gather, warp 4 MMA, warps 5-12 epilogue
 constexpr int kEpilogueWarps = 8;                         // two per TMEM lane quarter, half of the columns each
-constexpr int kRareWarp0 = kProducerWarps + 1 + kEpilogueWarps;  // warps 13-16 sum the rare entries of the tile's rows
+constexpr int kRareWarp0 = kProducerWarps + 1 + kEpilogueWarps;  // warps 13-18 sum the rare entries of the tile's rows
 constexpr int kRareWarps = 6;
-constexpr int kRingWarp = kRareWarp0 + kRareWarps;  // warp 17: one thread feeds the pair-buffer ring
+constexpr int kRingWarp = kRareWarp0 + kRareWarps;  // warp 19: one thread feeds the pair-buffer ring
 constexpr int kThreads = (kRingWarp + 1) * 32;
 constexpr uint32_t kATile = kTM * 128;  // 128 rows x 128 bytes
 
@@ -1021,7 +1021,7 @@ __global__ void __launch_bounds__(kThreads, 1) gx_conv_kernel(const __grid_const
         const bool has_rare = KIND == kKindStationary && a.rare_rs != nullptr && !(a.ablate & 2);
         if (has_rare) {
             const int rw = warp - kRareWarp0;
-            const int rt = rw * 32 + lane;  // thread of the four rare warps
+            const int rt = rw * 32 + lane;  // thread of the rare-sum warps
             const int LP = a.rare_lp;
             const int NG = kRareWarps * 32 / LP;  // lane groups; group g owns rows g, g + NG, g + 2 NG, ... so that the
             const int g = rt / LP;              // pairs of one ring chunk (consecutive rows) spread over all groups
