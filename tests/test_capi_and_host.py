@@ -246,3 +246,18 @@ def test_weights_loader_resolves_full_open3d_signatures(tmp_path):
     assert "SAVED" in r.stdout, r.stderr[-2000:]
     with pytest.raises(Exception, match="not_an_open3d_op"):
         model.load_weights_file(str(tmp_path / "bad.pt"))
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm: compiled reference geometry + restated network, no GPU, no product code)
+    on a small cloud: one JSON line with the same metric / unit as the GPU arm, its own cpu_baseline and a zero-copy e2e."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--points", "20000",
+                          "--levels", "3", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "points/s" and line["value"] > 0
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1
+    assert line["cpu_baseline"]["kind"].startswith("reference") and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "libasr_b200" not in out.stderr  # the product library is not on this path
