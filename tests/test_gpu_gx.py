@@ -39,7 +39,9 @@ def test_split_half_format_roundtrip():
     assert gx.overflow() and not gx.overflow()  # saturation is reported once, then cleared
 
 
-@pytest.mark.parametrize("cin,cout", [(32, 64), (64, 64), (64, 32), (32, 32), (128, 128), (384, 128), (256, 256)])
+# (64, 48) / (128, 96): output rows whose 16-byte chunk count is not a power of two (general copy-out path)
+@pytest.mark.parametrize("cin,cout", [(32, 64), (64, 64), (64, 32), (32, 32), (128, 128), (384, 128), (256, 256),
+                                      (64, 48), (128, 96)])
 def test_within_grid_conv_matches_oracle(cin, cout):
     from asr_b200 import gx
     from oracle import ops_cpu
