@@ -39,8 +39,12 @@ const char* asr_last_error(void);
 /* number of kernels this library has launched since load (bench.py gpu_launches) */
 int64_t asr_kernel_launches(void);
 
-/* Library options.  "sparse_conv_output_stationary" (default 0): run the within-grid convolutions
- * that carry no importance through the output-stationary tensor-core kernel (sparse_conv_os.cu). */
+/* Development options (defaults are what the benchmarks and tests run; unknown names -> status 1).  No reference
+ * counterpart.  gx convolution kernel (csrc/spconv_gx.cu): "gx_acc_groups" (accumulator groups per TMEM buffer, 0 = as
+ * many as fit), "gx_single_tmem" (one TMEM buffer with two groups for 128-column shapes: half the rounding error, 2-10 %
+ * slower), "gx_one_team", "gx_tma_gather" (TMA tile::gather4 instead of cp.async row gathers), "gx_l1_gather",
+ * "gx_max_stages", "gx_ablate" (timing experiments only: results become garbage), "gx_trace" (instrumented build only);
+ * round-1 kernels: "conv_row_block_shift", "tc_ntile", "tc_stages", "tc_row_groups". */
 int asr_set_option(const char* name, int value);
 
 /* bytes reserved / in use / release threshold / high-water mark in use of the stream-ordered memory pool the
